@@ -1,0 +1,361 @@
+"""Layer program of the segmentation hot path (host side, Python).
+
+The engine turns one forward/backward of ``VNet3d`` / ``UNet3d`` / ``UNet2d`` into a sequence
+of calls on a *backend* whose methods map 1:1 onto the ``extern "C"`` entry points of
+``include/b200seg.h`` (``_abi.CudaBackend``).  It owns no arithmetic: every FLOP and every
+byte moved happens inside a backend op (= one hand-written sm_100a kernel launch).
+
+Data layout: activations are channels-last ``(N, D, H, W, C)`` views
+(2-D nets use ``D == 1``) with a channel pitch ``ld >= C`` so that producers write straight
+into slices of a skip-concat buffer (``torch.cat`` of VNet3d.py:74 / Unet3d.py:45 is never
+materialised).  Storage dtype ``T`` is bf16 (perf mode) or fp32 (parity mode); GroupNorm
+statistics, loss partial sums and weight gradients are fp32/fp64.
+
+Block algebra: a ``conv -> GroupNorm(8) -> Dropout(p) -> ReLU`` block of
+the reference (VNet3d.py:13-15, Unet3d.py:66-85) is executed as
+  conv kernel (raw output y + per-(n,c) sum / sum-of-squares in the epilogue)
+  -> gn_finalize (mean, rstd per (n,g); A = rstd*gamma*s, B = (beta - mean*rstd*gamma)*s per (n,c))
+  -> apply      (act = relu(y*A + B) [+ second branch] [+ residual]), written where the consumer wants it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+# conv kinds understood by backend.conv / backend.wgrad
+K3, K1, DOWN, UP = 0, 1, 2, 3
+GROUPS = 8
+GN_EPS = 1e-5
+P_DROP = 0.2
+
+
+@dataclass
+class Layer:
+    """One conv application (+ optional GroupNorm/Dropout/ReLU tail) and what backward needs."""
+    kind: int
+    wname: str
+    bname: Optional[str]
+    gname: Optional[str]            # GroupNorm prefix ("in_tr.bn1") or None
+    x: Tensor = None                # input activation view (N,D,H,W,Cin)
+    y: Tensor = None                # raw conv output (N,D',H',W',Cout)
+    coef: Tensor = None             # (N,Cout,2) fp32  A,B
+    mr: Tensor = None               # (N,G,2)   fp32  mean, rstd
+    scale: Optional[Tensor] = None  # (N,Cout) dropout scale or None
+
+
+def _taps(kind: int, dims: int) -> int:
+    if kind == K3:
+        return 27 if dims == 3 else 9
+    if kind == K1:
+        return 1
+    return 8 if dims == 3 else 4
+
+
+class Engine:
+    """Executes the layer program on ``backend``.  ``P`` maps reference state_dict names to
+    fp32 parameter tensors (App. A layout)."""
+
+    def __init__(self, backend, act_dtype: torch.dtype, dims: int):
+        self.be = backend
+        self.T = act_dtype
+        self.dims = dims
+        self.P: Dict[str, Tensor] = {}
+        self.masks: Optional[List[Tensor]] = None
+        self._mi = 0
+        self.layers: List[Layer] = []
+        self.grads: Dict[str, Tensor] = {}
+        self.saved: Dict[str, object] = {}
+        self.need_grad = True
+
+    # ---------------------------------------------------------------- allocation helpers
+    def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
+        return torch.empty((like.shape[0],) + tuple(sp) + (c,), dtype=dtype or self.T, device=like.device)
+
+    def zeros(self, shape, dtype, device) -> Tensor:
+        return torch.zeros(shape, dtype=dtype, device=device)
+
+    def _next_mask(self) -> Optional[Tensor]:
+        if self.masks is None:
+            return None
+        m = self.masks[self._mi]
+        self._mi += 1
+        return m
+
+    # ---------------------------------------------------------------- forward primitives
+    def conv_raw(self, kind: int, wname: str, bname: Optional[str], x: Tensor, y: Tensor,
+                 stats: Optional[Tensor] = None) -> None:
+        w = self.P[wname]
+        wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims)
+        bias = self.P[bname] if bname is not None else None
+        self.be.conv(kind, self.dims, x, wpk, bias, y, stats, None)
+
+    def conv_gn(self, kind: int, wname: str, bname: Optional[str], gname: str, x: Tensor,
+                out_sp: Sequence[int], cout: int) -> Layer:
+        """conv + stats + finalize.  The activation itself is produced later by ``apply``."""
+        L = Layer(kind, wname, bname, gname, x=x)
+        n = x.shape[0]
+        L.y = self.new(x, out_sp, cout)
+        stats = self.zeros((n, cout, 2), torch.float64, x.device)
+        self.conv_raw(kind, wname, bname, x, L.y, stats)
+        L.scale = self._next_mask()
+        L.coef = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
+        L.mr = torch.empty((n, GROUPS, 2), dtype=torch.float32, device=x.device)
+        vox = 1
+        for s in out_sp:
+            vox *= s
+        self.be.gn_finalize(stats, self.P[gname + ".weight"], self.P[gname + ".bias"], L.scale, vox,
+                            GROUPS, GN_EPS, L.coef, L.mr)
+        self.layers.append(L)
+        return L
+
+    def act(self, L: Layer, out: Tensor, L2: Optional[Layer] = None, res: Optional[Tensor] = None) -> Tensor:
+        self.be.apply(L.y, L.coef, L2.y if L2 is not None else None, L2.coef if L2 is not None else None, res, out)
+        return out
+
+    # ---------------------------------------------------------------- backward primitives
+    def _grad_view(self, name: str) -> Tensor:
+        return self.grads[name]
+
+    def bwd_layer(self, L: Layer, g_act: Tensor, need_dx: bool, dx_out: Optional[Tensor] = None,
+                  dx_addend: Optional[Tensor] = None) -> Optional[Tensor]:
+        """Backward of one conv(+GN/drop/ReLU) application.  ``g_act`` is the gradient w.r.t.
+        the layer's activation output (or w.r.t. the raw conv output when the layer has no
+        GroupNorm).  Returns the gradient w.r.t. the layer input (written to ``dx_out``)."""
+        be = self.be
+        n, cout = L.y.shape[0], L.y.shape[-1]
+        dev = L.y.device
+        vox = L.y.numel() // (n * cout)
+        if L.gname is not None:
+            sums = self.zeros((n, cout, 3), torch.float64, dev)
+            be.gn_bwd_reduce(g_act, L.y, L.coef, sums)
+            coef3 = torch.empty((n, cout, 3), dtype=torch.float32, device=dev)
+            be.gn_bwd_finalize(sums, L.mr, self.P[L.gname + ".weight"], L.scale, vox, GROUPS, coef3,
+                               self._grad_view(L.gname + ".weight"), self._grad_view(L.gname + ".bias"),
+                               self._grad_view(L.bname) if L.bname is not None else None)
+            dy = torch.empty(L.y.shape, dtype=self.T, device=dev)
+            be.gn_bwd_apply(g_act, L.y, L.coef, coef3, dy)
+        else:
+            dy = g_act
+            if L.bname is not None:
+                be.colsum(dy, self._grad_view(L.bname))
+        w = self.P[L.wname]
+        taps = _taps(L.kind, self.dims)
+        cin = L.x.shape[-1]
+        if L.kind == UP:
+            dwp = self.zeros((taps, cout, cin), torch.float32, dev)
+            be.wgrad(DOWN, self.dims, dy, L.x, dwp)          # a = fine side (dy), b = coarse side (x)
+        else:
+            dwp = self.zeros((taps, cin, cout), torch.float32, dev)
+            be.wgrad(L.kind, self.dims, L.x, dy, dwp)
+        be.unpack_wgrad(dwp, self._grad_view(L.wname), L.kind, self.dims)
+        if not need_dx:
+            return None
+        wd = be.pack_weight(w, L.kind, "dgrad", self.T, self.dims)
+        dkind = {K3: K3, K1: K1, DOWN: UP, UP: DOWN}[L.kind]
+        if dx_out is None:
+            dx_out = torch.empty(L.x.shape, dtype=self.T, device=dev)
+        be.conv(dkind, self.dims, dy, wd, None, dx_out, None, dx_addend)
+        return dx_out
+
+    def alloc_grads(self, device) -> Tensor:
+        """One flat fp32 bucket; ``self.grads`` are views in state_dict order (the bucket is
+        what the data-parallel all-reduce sums)."""
+        total = sum(p.numel() for p in self.P.values())
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        self.grads = {}
+        for name, p in self.P.items():
+            self.grads[name] = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        return flat
+
+    # ================================================================== VNet3d
+    def vnet3d_forward(self, P: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]],
+                       need_grad: bool) -> Tuple[Tensor, Tensor]:
+        """VNet3d.forward (reference networks/VNet3d.py:129-158).  ``x``: (N,Cin,D,H,W) fp32.
+        Returns channels-last-strided (N,ncls,D,H,W) fp32 logits and probs."""
+        self.P, self.masks, self._mi, self.layers, self.need_grad = P, masks, 0, [], need_grad
+        sv = self.saved = {}
+        n, cin = x.shape[0], x.shape[1]
+        sp0 = tuple(x.shape[2:])
+        xin = x.permute(0, 2, 3, 4, 1)
+        if cin != 1:
+            xin = xin.contiguous()
+        f = P["in_tr.conv1.weight"].shape[0]
+        sps = [sp0]
+        for _ in range(4):
+            sps.append(tuple(s // 2 for s in sps[-1]))
+        ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
+        # skip-concat buffers of the four UpTransitions: [up | skip], VNet3d.py:74
+        cats = [self.new(x, sps[i], 2 * ch[i]) for i in range(4)]
+        skips = [cats[i][..., ch[i]:] for i in range(4)]
+
+        # ---- InputTransition3d (VNet3d.py:34-43): one bn1 serves both branches
+        La = self.conv_gn(K3, "in_tr.conv1.weight", "in_tr.conv1.bias", "in_tr.bn1", xin, sp0, f)
+        Lb = self.conv_gn(K1, "in_tr.conv2.weight", "in_tr.conv2.bias", "in_tr.bn1", xin, sp0, f)
+        out = self.act(La, skips[0], L2=Lb)
+        sv["in_tr"] = (La, Lb)
+
+        # ---- DownTransition3d x4 (VNet3d.py:55-59)
+        nconvs = {"down_tr32": 2, "down_tr64": 3, "down_tr128": 3, "down_tr256": 3}
+        for i, name in enumerate(["down_tr32", "down_tr64", "down_tr128", "down_tr256"]):
+            co, sp = ch[i + 1], sps[i + 1]
+            Ld = self.conv_gn(DOWN, name + ".down_conv.weight", name + ".down_conv.bias", name + ".bn1", out, sp, co)
+            down = self.act(Ld, self.new(x, sp, co))
+            h, ops = down, []
+            for j in range(nconvs[name]):
+                Lo = self.conv_gn(K3, f"{name}.ops.{j}.conv1.weight", f"{name}.ops.{j}.conv1.bias",
+                                  f"{name}.ops.{j}.bn1", h, sp, co)
+                ops.append(Lo)
+                last = j == nconvs[name] - 1
+                if last:
+                    dst = skips[i + 1] if i + 1 < 4 else self.new(x, sp, co)
+                    h = self.act(Lo, dst, res=down)                     # torch.add(out, down), VNet3d.py:58
+                else:
+                    h = self.act(Lo, self.new(x, sp, co))
+            sv[name] = (Ld, ops)
+            out = h
+
+        # ---- UpTransition3d x4 (VNet3d.py:72-80)
+        nconvs = {"up_tr256": 3, "up_tr128": 3, "up_tr64": 2, "up_tr32": 1}
+        for i, name in zip((3, 2, 1, 0), ["up_tr256", "up_tr128", "up_tr64", "up_tr32"]):
+            co, sp = ch[i], sps[i]
+            Lu = self.conv_gn(UP, name + ".up_conv.weight", name + ".up_conv.bias", name + ".bn", out, sp, co)
+            self.act(Lu, cats[i][..., :co])                              # left half of the concat
+            Lc = self.conv_gn(K1, name + ".conv.weight", name + ".conv.bias", name + ".bn", cats[i], sp, co)
+            xcat = self.act(Lc, self.new(x, sp, co))
+            h, ops = xcat, []
+            for j in range(nconvs[name]):
+                Lo = self.conv_gn(K3, f"{name}.ops.{j}.conv1.weight", f"{name}.ops.{j}.conv1.bias",
+                                  f"{name}.ops.{j}.bn1", h, sp, co)
+                ops.append(Lo)
+                last = j == nconvs[name] - 1
+                h = self.act(Lo, self.new(x, sp, co), res=xcat if last else None)   # VNet3d.py:79
+            sv[name] = (Lu, Lc, ops)
+            out = h
+
+        # ---- OutputTransition3d (VNet3d.py:90-99)
+        ncls = P["out_tr.conv.weight"].shape[0]
+        logits = self.new(x, sp0, ncls, dtype=torch.float32)
+        Lh = Layer(K1, "out_tr.conv.weight", "out_tr.conv.bias", None, x=out, y=logits)
+        self.conv_raw(K1, Lh.wname, Lh.bname, out, logits)
+        probs = torch.empty_like(logits)
+        self.be.head_probs(logits, probs)
+        sv["head"] = Lh
+        return logits.permute(0, 4, 1, 2, 3), probs.permute(0, 4, 1, 2, 3)
+
+    def vnet3d_backward(self, g_logits: Tensor) -> Tensor:
+        """Gradients of all 128 parameters given d loss / d logits ((N,D,H,W,ncls) fp32,
+        channels-last).  Returns the flat fp32 bucket; ``self.grads`` holds the views."""
+        sv = self.saved
+        flat = self.alloc_grads(g_logits.device)
+        Lh: Layer = sv["head"]
+        g = self.bwd_layer(Lh, g_logits, True)
+        gskip: List[Optional[Tensor]] = [None] * 4
+        for i, name in zip((0, 1, 2, 3), ["up_tr32", "up_tr64", "up_tr128", "up_tr256"]):
+            Lu, Lc, ops = sv[name]
+            g_out = g                                    # d/d(out) ; out = ops(xcat) + xcat
+            gh = g_out
+            for j in reversed(range(len(ops))):
+                gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None)
+            gcat = self.bwd_layer(Lc, gh, True)          # (N,..,2*co)
+            co = Lu.y.shape[-1]
+            gskip[i] = gcat[..., co:]
+            g = self.bwd_layer(Lu, gcat[..., :co], True)
+        for i, name in zip((3, 2, 1, 0), ["down_tr256", "down_tr128", "down_tr64", "down_tr32"]):
+            Ld, ops = sv[name]
+            g_out = g
+            gh = g_out
+            for j in reversed(range(len(ops))):
+                gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None)
+            g = self.bwd_layer(Ld, gh, True, dx_addend=gskip[i])
+        La, Lb = sv["in_tr"]
+        self.bwd_layer(La, g, False)
+        self.bwd_layer(Lb, g, False)
+        return flat
+
+    # ================================================================== UNet3d / UNet2d
+    def unet_forward(self, P: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]],
+                     need_grad: bool) -> Tuple[Tensor, Tensor]:
+        """UNet3d.forward / UNet2d.forward (reference networks/Unet3d.py:36-62, Unet2d.py:36-62)."""
+        self.P, self.masks, self._mi, self.layers, self.need_grad = P, masks, 0, [], need_grad
+        sv = self.saved = {}
+        dims = self.dims
+        n, cin = x.shape[0], x.shape[1]
+        if dims == 3:
+            sp0 = tuple(x.shape[2:])
+            xin = x.permute(0, 2, 3, 4, 1)
+        else:
+            sp0 = (1,) + tuple(x.shape[2:])
+            xin = x.permute(0, 2, 3, 1).unsqueeze(1)
+        if cin != 1:
+            xin = xin.contiguous()
+        f = P["encoder1.enc1conv1.weight"].shape[0]
+        ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
+        sps = [sp0]
+        for _ in range(4):
+            s = sps[-1]
+            sps.append((s[0] // 2 if dims == 3 else 1, s[1] // 2, s[2] // 2))
+        cats = [self.new(x, sps[i], 2 * ch[i]) for i in range(4)]
+
+        def block(mod: str, name: str, h: Tensor, sp, co: int, dst: Tensor):
+            L1 = self.conv_gn(K3, f"{mod}.{name}conv1.weight", None, f"{mod}.{name}norm1", h, sp, co)
+            a1 = self.act(L1, self.new(x, sp, co))
+            L2 = self.conv_gn(K3, f"{mod}.{name}conv2.weight", None, f"{mod}.{name}norm2", a1, sp, co)
+            a2 = self.act(L2, dst)
+            sv[mod] = (L1, L2)
+            return a2
+
+        h = xin
+        encs = []
+        for i in range(4):
+            e = block(f"encoder{i + 1}", f"enc{i + 1}", h, sps[i], ch[i], cats[i][..., ch[i]:])
+            encs.append(e)
+            h = self.new(x, sps[i + 1], ch[i])
+            self.be.pool_fwd(e, h, dims)                                   # nn.MaxPool(2,2), Unet3d.py:18-24
+            sv[f"pool{i + 1}"] = (e, h)
+        h = block("bottleneck", "bottleneck", h, sps[4], ch[4], self.new(x, sps[4], ch[4]))
+        for i in (3, 2, 1, 0):
+            k = i + 1
+            Lu = Layer(UP, f"upconv{k}.weight", f"upconv{k}.bias", None, x=h, y=cats[i][..., :ch[i]])
+            self.conv_raw(UP, Lu.wname, Lu.bname, h, Lu.y)                 # no norm/act, Unet3d.py:44
+            sv[f"upconv{k}"] = Lu
+            h = block(f"decoder{k}", f"dec{k}", cats[i], sps[i], ch[i], self.new(x, sps[i], ch[i]))
+        ncls = P["conv.weight"].shape[0]
+        logits = self.new(x, sp0, ncls, dtype=torch.float32)
+        Lh = Layer(K1, "conv.weight", "conv.bias", None, x=h, y=logits)
+        self.conv_raw(K1, Lh.wname, Lh.bname, h, logits)
+        probs = torch.empty_like(logits)
+        self.be.head_probs(logits, probs)
+        sv["head"] = Lh
+        if dims == 3:
+            return logits.permute(0, 4, 1, 2, 3), probs.permute(0, 4, 1, 2, 3)
+        return logits[:, 0].permute(0, 3, 1, 2), probs[:, 0].permute(0, 3, 1, 2)
+
+    def unet_backward(self, g_logits: Tensor) -> Tensor:
+        sv = self.saved
+        flat = self.alloc_grads(g_logits.device)
+        g = self.bwd_layer(sv["head"], g_logits, True)
+        genc: List[Optional[Tensor]] = [None] * 4
+        for i in (0, 1, 2, 3):
+            k = i + 1
+            L1, L2 = sv[f"decoder{k}"]
+            g1 = self.bwd_layer(L2, g, True)
+            gcat = self.bwd_layer(L1, g1, True)
+            co = L2.y.shape[-1]
+            genc[i] = gcat[..., co:]
+            g = self.bwd_layer(sv[f"upconv{k}"], gcat[..., :co], True)
+        L1, L2 = sv["bottleneck"]
+        g = self.bwd_layer(L1, self.bwd_layer(L2, g, True), True)
+        for i in (3, 2, 1, 0):
+            e, pooled = sv[f"pool{i + 1}"]
+            ge = torch.empty(e.shape, dtype=self.T, device=e.device)
+            self.be.pool_bwd(e, g, genc[i], ge, self.dims)               # + gradient from the skip concat
+            L1, L2 = sv[f"encoder{i + 1}"]
+            g1 = self.bwd_layer(L2, ge, True)
+            g = self.bwd_layer(L1, g1, i > 0)
+        return flat

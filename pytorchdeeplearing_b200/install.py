@@ -1,0 +1,43 @@
+"""Patch the drop-in into an imported reference tree.
+
+The reference wrappers bind the classes at import time (``from networks.VNet3d import VNet3d``
+model/modelVNet.py:2-4, model/modelUnet.py:2-4; losses model/modelVNet.py:7-8), so ``install``
+rebinds those names in whichever of ``networks``, ``networks.*``, ``model.modelVNet``,
+``model.modelUnet``, ``model.losses`` are already imported (and in ``sys.modules`` entries
+imported later via the same names).  ``uninstall`` restores the originals.
+"""
+from __future__ import annotations
+
+import sys
+
+_SAVED = []
+
+_NET_NAMES = ("VNet3d", "UNet3d", "UNet2d")
+_LOSS_NAMES = ("BinaryDiceLoss", "BinaryCrossEntropyLoss", "BinaryFocalLoss", "BinaryCrossEntropyDiceLoss",
+               "MutilCrossEntropyLoss", "MutilFocalLoss", "MutilDiceLoss", "MutilCrossEntropyDiceLoss")
+_MODULES = ("networks", "networks.VNet3d", "networks.Unet3d", "networks.Unet2d", "model", "model.losses",
+            "model.modelVNet", "model.modelUnet")
+
+
+def install() -> int:
+    """Rebind the reference's names to the B200 implementations. Returns the number of bindings changed."""
+    from . import networks as nets, losses
+    table = {n: getattr(nets, n) for n in _NET_NAMES}
+    table.update({n: getattr(losses, n) for n in _LOSS_NAMES})
+    count = 0
+    for modname in _MODULES:
+        mod = sys.modules.get(modname)
+        if mod is None:
+            continue
+        for name, obj in table.items():
+            if hasattr(mod, name) and getattr(mod, name) is not obj:
+                _SAVED.append((mod, name, getattr(mod, name)))
+                setattr(mod, name, obj)
+                count += 1
+    return count
+
+
+def uninstall() -> None:
+    while _SAVED:
+        mod, name, obj = _SAVED.pop()
+        setattr(mod, name, obj)

@@ -1,0 +1,175 @@
+"""Drop-in hot-path losses of the reference ``model/losses.py`` (same class names, constructor
+arguments and ``forward(y_pred_logits, y_true) -> 0-dim fp32 tensor``).
+
+Each loss is ONE fused reduction pass over logits + labels (``b200seg_loss_partials``), a
+scalar finalize (``b200seg_loss_finalize``) and ONE elementwise backward pass writing
+d loss / d logits (``b200seg_loss_bwd``) -- closed forms of SURVEY.md App. C -- instead of
+the ~10-15 elementwise/reduce launches of the reference.  Under data parallelism the
+partial sums are all-reduced so the value and gradient equal the reference evaluated on the
+GLOBAL batch (Dice sums run over batch and space, model/losses.py:50-51,315-317).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import runtime
+
+DICE, CE, FOCAL = 1, 2, 4
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, terms, alpha, gamma, alpha_f):
+        be = runtime.get_backend(logits)
+        c = logits.shape[1]
+        # channels-last fp32 view of the logits (free when they come from the drop-in networks)
+        z = logits.detach()
+        perm = (0, 2, 3, 4, 1) if z.dim() == 5 else (0, 2, 3, 1)
+        z = z.permute(*perm)
+        if z.dtype != torch.float32:
+            z = z.float()                               # losses.py:47 ``.float()``
+        if not z.is_contiguous():
+            z = z.contiguous()
+        t = labels.detach()
+        if t.dtype != torch.int64:
+            t = t.long()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        if t.numel() * c != z.numel():
+            raise RuntimeError(f"label shape {tuple(labels.shape)} does not match logits {tuple(logits.shape)}")
+        dev = z.device
+        part = torch.zeros(3 * c + 3 if c > 1 else 6, dtype=torch.float64, device=dev)
+        be.loss_partials(z, t, float(gamma), float(alpha_f), part)
+        enabled, group = runtime.dp_state()
+        if enabled:
+            import torch.distributed as dist
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        lcoef = torch.empty(2 * c + 3 if c > 1 else 5, dtype=torch.float32, device=dev)
+        if alpha is None:
+            alpha = torch.ones(c, dtype=torch.float32, device=dev)
+        else:
+            alpha = torch.as_tensor(alpha, dtype=torch.float32, device=dev)
+        be.loss_finalize(part, c, terms, alpha, float(gamma), float(alpha_f), loss, lcoef)
+        ctx.save_for_backward(z, t, lcoef)
+        ctx.perm = perm
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, t, lcoef = ctx.saved_tensors
+        be = runtime.get_backend(z)
+        dz = torch.empty_like(z)
+        g = gout.detach().to(torch.float32).reshape(1).contiguous()
+        be.loss_bwd(z, t, lcoef, g, dz)
+        inv = (0, 4, 1, 2, 3) if z.dim() == 5 else (0, 3, 1, 2)
+        return dz.permute(*inv), None, None, None, None, None
+
+
+def _call(logits, labels, terms, alpha=None, gamma=2.0, alpha_f=0.25):
+    return _FusedLoss.apply(logits, labels, terms, alpha, gamma, alpha_f)
+
+
+# ------------------------------------------------------------------------------ binary (sigmoid head)
+class BinaryDiceLoss(nn.Module):
+    """reference model/losses.py:33-53"""
+
+    def __init__(self):
+        super().__init__()
+        self.smooth = 1e-5
+        self.eps = 1e-7
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, DICE)
+
+
+class BinaryCrossEntropyLoss(nn.Module):
+    """reference model/losses.py:129-147"""
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, CE)
+
+
+class BinaryFocalLoss(nn.Module):
+    """reference model/losses.py:150-181 (alpha applied to both classes)"""
+
+    def __init__(self, alpha=0.25, gamma=2):
+        super().__init__()
+        self.alpha = alpha
+        self.gamma = gamma
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, FOCAL, gamma=self.gamma, alpha_f=self.alpha)
+
+
+class BinaryCrossEntropyDiceLoss(nn.Module):
+    """reference model/losses.py:184-197"""
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, DICE | CE)
+
+
+class BinaryDiceFocalLoss(nn.Module):
+    """BinaryDiceLoss + BinaryFocalLoss() in one pass (BASELINE.json config 5 "Dice+focal";
+    the reference has no class for it -- SURVEY.md a14)."""
+
+    def __init__(self, alpha=0.25, gamma=2):
+        super().__init__()
+        self.alpha = alpha
+        self.gamma = gamma
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, DICE | FOCAL, gamma=self.gamma, alpha_f=self.alpha)
+
+
+# ------------------------------------------------------------------------------ multi-class (softmax head)
+class MutilCrossEntropyLoss(nn.Module):
+    """reference model/losses.py:247-260 (``alpha`` stored but unused, as in the reference)"""
+
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = alpha
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, CE)
+
+
+class MutilFocalLoss(nn.Module):
+    """reference model/losses.py:263-285 (``alpha`` / ``torch`` stored but unused)"""
+
+    def __init__(self, alpha, gamma=2, torch=True):
+        super().__init__()
+        self.gamma = gamma
+        self.alpha = alpha
+        self.torch = torch
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, FOCAL, gamma=self.gamma)
+
+
+class MutilDiceLoss(nn.Module):
+    """reference model/losses.py:288-325 (negative generalised Dice over present classes)"""
+
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = alpha
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, DICE, alpha=self.alpha)
+
+
+class MutilCrossEntropyDiceLoss(nn.Module):
+    """reference model/losses.py:328-342"""
+
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = alpha
+
+    def forward(self, y_pred_logits, y_true):
+        return _call(y_pred_logits, y_true, DICE | CE, alpha=self.alpha)
+
+
+__all__ = ["BinaryDiceLoss", "BinaryCrossEntropyLoss", "BinaryFocalLoss", "BinaryCrossEntropyDiceLoss",
+           "BinaryDiceFocalLoss", "MutilCrossEntropyLoss", "MutilFocalLoss", "MutilDiceLoss",
+           "MutilCrossEntropyDiceLoss"]
