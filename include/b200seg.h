@@ -1,0 +1,140 @@
+/*
+ * b200seg.h -- C ABI of the B200-native (sm_100a) segmentation hot path.
+ *
+ * The reference (junqiangchen/PytorchDeepLearing) has NO native code and NO FFI: its "plugin
+ * boundary" is the Python nn.Module protocol used by model/modelVNet.py:490-497,546-548,580-593
+ * and model/modelUnet.py:46,270,490,793.  The Python drop-in
+ * (pytorchdeeplearing_b200/) keeps that protocol and binds the entry points below through ctypes
+ * (pytorchdeeplearing_b200/_abi.py).  Each entry point replaces the ATen call sites cited next to
+ * it (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - returns 0 on success, a negative B200SEG_E* code otherwise (b200seg_last_error() has text);
+ *   - never allocates, frees or synchronises: caller owns every buffer (torch caching allocator),
+ *     every launch goes to the cudaStream_t passed in, on CUDA device `device`;
+ *   - re-entrant and thread-safe (autograd runs backward on its own thread);
+ *   - activations are channels-last tensors (N, D, H, W, C) with a channel pitch `ld >= C`
+ *     (elements) so that a producer can write into a slice of a skip-concat buffer; 2-D networks
+ *     use D == 1 and `dims == 2`.
+ */
+#ifndef B200SEG_H
+#define B200SEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_VERSION 100
+
+#define B200SEG_OK 0
+#define B200SEG_EINVAL (-1)   /* bad argument / unsupported combination */
+#define B200SEG_ECUDA (-2)    /* CUDA runtime error (text in b200seg_last_error) */
+
+#define B200SEG_F32 0
+#define B200SEG_BF16 1
+#define B200SEG_BF16_TC 2 /* weights only: bf16 packed [tap][N][K] (K-major) for the tcgen05/TMA conv path */
+
+/* conv kinds */
+#define B200SEG_K3 0    /* 3x3x3 (dims==3) or 1x3x3 (dims==2), stride 1, zero pad 1 */
+#define B200SEG_K1 1    /* 1x1x1 */
+#define B200SEG_DOWN 2  /* k=2, s=2 convolution (space-to-depth GEMM) */
+#define B200SEG_UP 3    /* k=2, s=2 transposed convolution (GEMM + depth-to-space) */
+
+/* loss terms (bitmask) */
+#define B200SEG_LOSS_DICE 1
+#define B200SEG_LOSS_CE 2
+#define B200SEG_LOSS_FOCAL 4
+
+typedef struct b200seg_tensor {
+  void* ptr;       /* device pointer to element (0,0,0,0,0) */
+  int32_t n, d, h, w, c;
+  int64_t ld;      /* channel pitch in elements: element (n,d,h,w,c) is at (((n*d_+d)*h_+h)*w_+w)*ld + c */
+  int32_t dtype;   /* B200SEG_F32 | B200SEG_BF16 */
+} b200seg_tensor;
+
+typedef void* b200seg_stream; /* cudaStream_t */
+
+int b200seg_version(void);
+const char* b200seg_last_error(void);
+/* one-time per-process/per-device setup (opt-in shared memory sizes); safe to call repeatedly */
+int b200seg_init(int device);
+
+/* ---- weights --------------------------------------------------------------------------------
+ * out[t][k][n2][n1] = w[tmap(t)*st + k*sk + n2*sn2 + n1*sn1], tmap(t) = flip ? T-1-t : t.
+ * Turns nn.Conv3d (Co,Ci,k,k,k) / nn.ConvTranspose3d (Ci,Co,k,k,k) parameters
+ * (networks/VNet3d.py:8,28,29,49,65,70,88; Unet3d.py:26-34,67-81) into the [tap][K][N] operand
+ * layouts of b200seg_conv (forward and data-gradient forms). */
+int b200seg_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N2, int N1, int64_t st,
+                        int64_t sk, int64_t sn2, int64_t sn1, int flip, int device, b200seg_stream stream);
+/* grad[t*st + k*sk + n*sn] = dwp[t][k][n]  (inverse permutation, fp32 -> parameter .grad layout) */
+int b200seg_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, int64_t st, int64_t sk, int64_t sn,
+                         int device, b200seg_stream stream);
+
+/* ---- convolution family (replaces F.conv3d / F.conv_transpose3d / F.conv2d, call sites above;
+ * the data-gradient half of aten::convolution_backward runs through the same entry with
+ * dgrad-packed weights).
+ *   y = conv_kind(x, wpk) [+ bias] [+ addend];   stats[n][c] += {sum, sum of squares} of (conv + bias)
+ * x: F32|T, wpk: T (dtype w_dtype), y: T|F32, addend: same dtype as y or NULL, bias fp32 or NULL,
+ * stats: double [N][Cout][2] or NULL (GroupNorm statistics fused into the epilogue: nn.GroupNorm,
+ * VNet3d.py:9,30,50,66; Unet3d.py:73,82). */
+int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, int w_dtype, const float* bias,
+                 const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device,
+                 b200seg_stream stream);
+
+/* 1 if b200seg_conv runs (kind, Cin -> Cout) on the tcgen05 + TMA path when given bf16 activations and
+ * B200SEG_BF16_TC weights ([tap][Cout][Cin] for the forward form, [tap'][Cin][Cout], taps flipped, for the
+ * data-gradient form); 0 -> pack [tap][K][N] and use the CUDA-core path. */
+int b200seg_conv_tc_eligible(int kind, int cin, int cout);
+
+/* weight-gradient half of aten::convolution_backward:
+ *   dwp[t][ka][kb] += sum_{n,o} a[n, o*s + t - p, ka] * b[n, o, kb]      (fp32, caller zero-fills)
+ * kind in {K3, K1, DOWN}; for the transposed conv call with kind = DOWN, a = dy (fine), b = x. */
+int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+                  b200seg_stream stream);
+
+/* ---- GroupNorm(8) + Dropout(p) + ReLU tail (nn.GroupNorm / nn.Dropout3d / nn.ReLU, VNet3d.py:9-11,14;
+ * Unet3d.py:73-75) split into statistics (conv epilogue) -> finalize -> apply */
+int b200seg_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
+                        int groups, int64_t vox, float eps, float* coef /*[N][C][2]*/, float* mr /*[N][G][2]*/,
+                        int device, b200seg_stream stream);
+/* out = relu(y1*A1+B1) [+ relu(y2*A2+B2)] [+ res]   (torch.add residuals VNet3d.py:41,58,79) */
+int b200seg_apply(const b200seg_tensor* y1, const float* coef1, const b200seg_tensor* y2, const float* coef2,
+                  const b200seg_tensor* res, const b200seg_tensor* out, int device, b200seg_stream stream);
+/* native_group_norm_backward + threshold_backward + dropout backward:
+ *   sums[n][c] += { sum g*m, sum g*m*y, sum y },  m = [y*A+B > 0] */
+int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums,
+                          int device, b200seg_stream stream);
+int b200seg_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
+                            int groups, int64_t vox, float* coef3 /*[N][C][3]*/, float* dgamma /* += */,
+                            float* dbeta /* += */, float* dbias /* = or NULL */, int device, b200seg_stream stream);
+/* dy = (y*A+B > 0 ? g*P : 0) + y*Q + R */
+int b200seg_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
+                         const b200seg_tensor* dy, int device, b200seg_stream stream);
+/* out[c] = sum_{n,d,h,w} dy[...,c]   (bias gradient of convs without GroupNorm) */
+int b200seg_colsum(const b200seg_tensor* dy, float* out, int device, b200seg_stream stream);
+
+/* ---- nn.MaxPool3d/2d(2,2) (Unet3d.py:18-24) */
+int b200seg_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, int device, b200seg_stream stream);
+int b200seg_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* g_out, const b200seg_tensor* addend,
+                     const b200seg_tensor* g_x, int dims, int device, b200seg_stream stream);
+
+/* ---- head activation: torch.sigmoid / torch.softmax(dim=1) (VNet3d.py:95-98; Unet3d.py:58-61) */
+int b200seg_head_probs(const float* logits, float* probs, int64_t nvox, int C, int device, b200seg_stream stream);
+
+/* ---- losses (model/losses.py:33-53,129-197,247-342), logits fp32 channels-last [nvox][C], labels int64
+ * part (double, += ): C>1: I_c[C], P_c[C], Cnt_c[C], sum_nll, sum_focal, V ; C==1: I, P, T, sum_bce, sum_focal, V */
+int b200seg_loss_partials(const float* logits, const int64_t* labels, int64_t nvox, int C, float gamma, float alpha_f,
+                          double* part, int device, b200seg_stream stream);
+/* lcoef (fp32): C>1: a_c[C], b_c[C], ce_scale, focal_scale, gamma ; C==1: a, b, bce_scale, focal_scale, gamma */
+int b200seg_loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f,
+                          float* loss, float* lcoef, int device, b200seg_stream stream);
+int b200seg_loss_bwd(const float* logits, const int64_t* labels, int64_t nvox, int C, const float* lcoef,
+                     const float* gscale, float* dlogits, int device, b200seg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H */

@@ -1,0 +1,281 @@
+"""ctypes binding of ``libb200seg.so`` (C ABI: ``include/b200seg.h``) -- the ONLY product backend.
+
+``CudaBackend`` exposes one method per ``b200seg_*`` entry point with torch tensors as
+arguments; it extracts raw device pointers / shapes / pitches and passes the current CUDA
+stream.  PyTorch is plumbing here (allocator, streams); no torch operator computes anything.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import torch
+
+K3, K1, DOWN, UP = 0, 1, 2, 3
+F32, BF16, BF16_TC = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200seg.so")
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("ld", C.c_int64), ("dtype", C.c_int32)]
+
+
+_PT = C.POINTER(TensorDesc)
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+_SIGNATURES = {
+    "b200seg_version": ([], C.c_int),
+    "b200seg_last_error": ([], C.c_char_p),
+    "b200seg_init": ([_i], C.c_int),
+    "b200seg_pack_weight": ([_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp], C.c_int),
+    "b200seg_unpack_wgrad": ([_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp], C.c_int),
+    "b200seg_conv": ([_i, _i, _PT, _vp, _i, _vp, _PT, _vp, _PT, _i, _vp], C.c_int),
+    "b200seg_conv_tc_eligible": ([_i, _i, _i], C.c_int),
+    "b200seg_wgrad": ([_i, _i, _PT, _PT, _vp, _i, _vp], C.c_int),
+    "b200seg_gn_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_apply": ([_PT, _vp, _PT, _vp, _PT, _PT, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_reduce": ([_PT, _PT, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_apply": ([_PT, _PT, _vp, _vp, _PT, _i, _vp], C.c_int),
+    "b200seg_colsum": ([_PT, _vp, _i, _vp], C.c_int),
+    "b200seg_pool_fwd": ([_PT, _PT, _i, _i, _vp], C.c_int),
+    "b200seg_pool_bwd": ([_PT, _PT, _PT, _PT, _i, _i, _vp], C.c_int),
+    "b200seg_head_probs": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
+    "b200seg_loss_partials": ([_vp, _vp, _i64, _i, _f, _f, _vp, _i, _vp], C.c_int),
+    "b200seg_loss_finalize": ([_vp, _i, _i, _vp, _f, _f, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_loss_bwd": ([_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp], C.c_int),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the in-tree library and declare every prototype.  Raises if it is missing:
+    there is no fallback implementation."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise RuntimeError(
+                f"{p} not found: build it with `python -m pytorchdeeplearing_b200.build` "
+                "(or __graft_entry__.build()). pytorchdeeplearing_b200 has no non-CUDA fallback.")
+        lib = C.CDLL(p)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if lib.b200seg_version() < 100:
+            raise RuntimeError("libb200seg.so is older than the Python binding")
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _desc(t: Optional[torch.Tensor]):
+    """(N,D,H,W,C) view with unit channel stride and pitch = stride of W -> TensorDesc."""
+    if t is None:
+        return None
+    if t.dim() != 5:
+        raise ValueError(f"expected (N,D,H,W,C), got {tuple(t.shape)}")
+    n, d, h, w, c = t.shape
+    sn, sd, sh, sw, sc = t.stride()
+    ld = sw if w > 1 else (sh // w if h > 1 else (sd // (h * w) if d > 1 else max(sn // (d * h * w), c)))
+    if c > 1 and sc != 1:
+        raise ValueError("channel stride must be 1 (channels-last)")
+    ok = (w == 1 or sw == ld) and (h == 1 or sh == ld * w) and (d == 1 or sd == ld * w * h) and \
+         (n == 1 or sn == ld * w * h * d)
+    if not ok or ld < c:
+        raise ValueError(f"tensor is not an NDHWC view with a channel pitch: shape {tuple(t.shape)} strides {t.stride()}")
+    return TensorDesc(t.data_ptr(), n, d, h, w, c, ld, _dt(t))
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _ref(d):
+    return None if d is None else C.byref(d)
+
+
+class PackedWeight:
+    """Packed conv operand + its layout code (B200SEG_F32 / BF16 = [tap][K][N]; BF16_TC = [tap][N][K] K-major
+    for the tcgen05 path).  Keeps what is needed to re-pack for the CUDA-core path."""
+    __slots__ = ("t", "code", "src", "kind", "which", "dims")
+
+    def __init__(self, t, code, src, kind, which, dims):
+        self.t, self.code, self.src, self.kind, self.which, self.dims = t, code, src, kind, which, dims
+
+
+class CudaBackend:
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pytorchdeeplearing_b200 needs a CUDA device (built for sm_100a); none is available "
+                               "and there is no CPU fallback")
+        self.lib = load_library()
+        self._inited = set()
+        # B200SEG_DISABLE_TC=1 forces every conv onto the CUDA-core implicit-GEMM kernels (debug / A-B timing)
+        self.use_tc = os.environ.get("B200SEG_DISABLE_TC", "0") != "1"
+
+    # ------------------------------------------------------------------ plumbing
+    def _ds(self, t: torch.Tensor):
+        dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        if dev not in self._inited:
+            self._check(self.lib.b200seg_init(dev))
+            self._inited.add(dev)
+        return dev, torch.cuda.current_stream(dev).cuda_stream
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.b200seg_last_error()
+            raise RuntimeError(f"libb200seg error {rc}: {msg.decode() if msg else ''}")
+
+    # ------------------------------------------------------------------ weights
+    def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True):
+        a, b = w.shape[0], w.shape[1]
+        t = w.numel() // (a * b)
+        dev, st = self._ds(w)
+        od = F32 if dtype == torch.float32 else BF16
+        code = od
+        tc = False
+        if allow_tc and self.use_tc and dtype == torch.bfloat16 and kind in (K3, K1):
+            cin, cout = (b, a) if which == "fwd" else (a, b)
+            tc = bool(self.lib.b200seg_conv_tc_eligible(kind, cin, cout))
+        if tc:
+            code = BF16_TC
+            if which == "fwd":     # W (Co,Ci,t) -> [t][co][ci]
+                out = torch.empty((t, a, b), dtype=dtype, device=w.device)
+                args = (t, a, 1, b, 1, b * t, 0, t, 0)
+            else:                  # [T-1-t][ci][co]
+                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
+                args = (t, b, 1, a, 1, t, 0, b * t, 1)
+        elif which == "fwd":
+            if kind == UP:      # W (Ci,Co,t) -> [ci][t*Co + co]
+                out = torch.empty((a, t * b), dtype=dtype, device=w.device)
+                args = (1, a, t, b, 0, b * t, 1, t, 0)
+            else:               # W (Co,Ci,t) -> [t][ci][co]
+                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
+                args = (t, b, 1, a, 1, t, 0, b * t, 0)
+        else:
+            if kind in (K3, K1):   # [T-1-t][co][ci]
+                out = torch.empty((t, a, b), dtype=dtype, device=w.device)
+                args = (t, a, 1, b, 1, b * t, 0, t, 1)
+            elif kind == DOWN:     # W (Co,Ci,t) -> [co][t*Ci + ci]
+                out = torch.empty((a, t * b), dtype=dtype, device=w.device)
+                args = (1, a, t, b, 0, b * t, 1, t, 0)
+            else:                  # UP: W (Ci,Co,t) -> [t][co][ci]
+                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
+                args = (t, b, 1, a, 1, t, 0, b * t, 0)
+        T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
+        self._check(self.lib.b200seg_pack_weight(w.data_ptr(), out.data_ptr(), od, T, K, N2, N1, s_t, s_k, s_n2, s_n1,
+                                                 flip, dev, st))
+        return PackedWeight(out, code, w, kind, which, dims)
+
+    def unpack_wgrad(self, dwp, grad, kind, dims):
+        t, k, n = dwp.shape
+        dev, st = self._ds(dwp)
+        # dwp[t][k][n] -> grad[n][k][t]  (gather kinds: (Co,Ci,t); UP: (Ci,Co,t))
+        self._check(self.lib.b200seg_unpack_wgrad(dwp.data_ptr(), grad.data_ptr(), t, k, n, 1, t, k * t, dev, st))
+
+    # ------------------------------------------------------------------ conv family
+    def conv(self, kind, dims, x, wpk, bias, y, stats, addend):
+        dev, st = self._ds(x)
+        if wpk.code == BF16_TC and not (x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16):
+            # tcgen05 path needs bf16 activations on both sides (e.g. a 16-channel fp32 network input)
+            wpk = self.pack_weight(wpk.src, wpk.kind, wpk.which, torch.bfloat16, wpk.dims, allow_tc=False)
+        dx, dy, da = _desc(x), _desc(y), _desc(addend)
+        self._check(self.lib.b200seg_conv(kind, dims, C.byref(dx), wpk.t.data_ptr(), wpk.code, _p(bias), C.byref(dy),
+                                          _p(stats), _ref(da), dev, st))
+
+    def wgrad(self, kind, dims, a, b, dwp):
+        dev, st = self._ds(a)
+        da, db = _desc(a), _desc(b)
+        self._check(self.lib.b200seg_wgrad(kind, dims, C.byref(da), C.byref(db), dwp.data_ptr(), dev, st))
+
+    # ------------------------------------------------------------------ GroupNorm
+    def gn_finalize(self, stats, gamma, beta, scale, vox, groups, eps, coef, mr):
+        dev, st = self._ds(stats)
+        n, c = stats.shape[0], stats.shape[1]
+        self._check(self.lib.b200seg_gn_finalize(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(scale), n, c,
+                                                 groups, vox, eps, coef.data_ptr(), mr.data_ptr(), dev, st))
+
+    def apply(self, y1, c1, y2, c2, res, out):
+        dev, st = self._ds(y1)
+        d1, d2, dr, do = _desc(y1), _desc(y2), _desc(res), _desc(out)
+        self._check(self.lib.b200seg_apply(C.byref(d1), c1.data_ptr(), _ref(d2), _p(c2), _ref(dr), C.byref(do), dev, st))
+
+    def gn_bwd_reduce(self, g, y, coef, sums):
+        dev, st = self._ds(y)
+        dg, dy = _desc(g), _desc(y)
+        self._check(self.lib.b200seg_gn_bwd_reduce(C.byref(dg), C.byref(dy), coef.data_ptr(), sums.data_ptr(), dev, st))
+
+    def gn_bwd_finalize(self, sums, mr, gamma, scale, vox, groups, coef3, dgamma, dbeta, dbias):
+        dev, st = self._ds(sums)
+        n, c = sums.shape[0], sums.shape[1]
+        self._check(self.lib.b200seg_gn_bwd_finalize(sums.data_ptr(), mr.data_ptr(), gamma.data_ptr(), _p(scale), n, c,
+                                                     groups, vox, coef3.data_ptr(), dgamma.data_ptr(),
+                                                     dbeta.data_ptr(), _p(dbias), dev, st))
+
+    def gn_bwd_apply(self, g, y, coef, coef3, dy):
+        dev, st = self._ds(y)
+        dg, dyy, dd = _desc(g), _desc(y), _desc(dy)
+        self._check(self.lib.b200seg_gn_bwd_apply(C.byref(dg), C.byref(dyy), coef.data_ptr(), coef3.data_ptr(),
+                                                  C.byref(dd), dev, st))
+
+    def colsum(self, dy, out):
+        dev, st = self._ds(dy)
+        d = _desc(dy)
+        self._check(self.lib.b200seg_colsum(C.byref(d), out.data_ptr(), dev, st))
+
+    # ------------------------------------------------------------------ pooling
+    def pool_fwd(self, x, out, dims):
+        dev, st = self._ds(x)
+        dx, do = _desc(x), _desc(out)
+        self._check(self.lib.b200seg_pool_fwd(C.byref(dx), C.byref(do), dims, dev, st))
+
+    def pool_bwd(self, x, g_out, addend, g_x, dims):
+        dev, st = self._ds(x)
+        dx, dg, da, do = _desc(x), _desc(g_out), _desc(addend), _desc(g_x)
+        self._check(self.lib.b200seg_pool_bwd(C.byref(dx), C.byref(dg), _ref(da), C.byref(do), dims, dev, st))
+
+    # ------------------------------------------------------------------ head + losses
+    def head_probs(self, logits, probs):
+        dev, st = self._ds(logits)
+        c = logits.shape[-1]
+        self._check(self.lib.b200seg_head_probs(logits.data_ptr(), probs.data_ptr(), logits.numel() // c, c, dev, st))
+
+    def loss_partials(self, logits, labels, gamma, alpha_f, part):
+        dev, st = self._ds(logits)
+        c = logits.shape[-1]
+        self._check(self.lib.b200seg_loss_partials(logits.data_ptr(), labels.data_ptr(), logits.numel() // c, c,
+                                                   gamma, alpha_f, part.data_ptr(), dev, st))
+
+    def loss_finalize(self, part, c, terms, alpha, gamma, alpha_f, loss, lcoef):
+        dev, st = self._ds(part)
+        self._check(self.lib.b200seg_loss_finalize(part.data_ptr(), c, terms, alpha.data_ptr(), gamma, alpha_f,
+                                                   loss.data_ptr(), lcoef.data_ptr(), dev, st))
+
+    def loss_bwd(self, logits, labels, lcoef, gscale, dlogits):
+        dev, st = self._ds(logits)
+        c = logits.shape[-1]
+        self._check(self.lib.b200seg_loss_bwd(logits.data_ptr(), labels.data_ptr(), logits.numel() // c, c,
+                                              lcoef.data_ptr(), gscale.data_ptr(), dlogits.data_ptr(), dev, st))

@@ -1,0 +1,229 @@
+// extern "C" surface of libb200seg.so (see include/b200seg.h for the contract).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200seg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in the other translation units
+int conv_generic(int kind, int dims, const b200seg_tensor* x, const void* wpk, int w_dtype, const float* bias,
+                 const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, cudaStream_t st);
+int conv_tc_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                      const b200seg_tensor* addend);
+int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
+            double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
+int conv_tc_init(int device);
+int conv_tc_channels_ok(int kind, int cin, int cout);
+int wgrad_generic(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+                  cudaStream_t st);
+int ew_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N2, int N1, long long st,
+                   long long sk, long long sn2, long long sn1, int flip, cudaStream_t s);
+int ew_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, long long st, long long sk, long long sn,
+                    cudaStream_t s);
+int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
+                   int groups, long long vox, float eps, float* coef, float* mr, cudaStream_t s);
+int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_tensor* y2, const float* c2,
+             const b200seg_tensor* res, const b200seg_tensor* out, int device, cudaStream_t s);
+int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,
+                     cudaStream_t s);
+int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
+                       int groups, long long vox, float* coef3, float* dgamma, float* dbeta, float* dbias,
+                       cudaStream_t s);
+int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
+                    const b200seg_tensor* dy, int device, cudaStream_t s);
+int ew_colsum(const b200seg_tensor* dy, float* out, int device, cudaStream_t s);
+int ew_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, int device, cudaStream_t s);
+int ew_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* go, const b200seg_tensor* addend,
+                const b200seg_tensor* gx, int dims, int device, cudaStream_t s);
+int ew_head_probs(const float* logits, float* probs, long long nvox_, int C, int device, cudaStream_t s);
+int loss_partials(const float* logits, const long long* labels, long long nvox_, int C, float gamma, float alpha_f,
+                  double* part, int device, cudaStream_t s);
+int loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f, float* loss,
+                  float* lcoef, cudaStream_t s);
+int loss_bwd(const float* logits, const long long* labels, long long nvox_, int C, const float* lcoef,
+             const float* gscale, float* dlogits, int device, cudaStream_t s);
+
+static bool valid_tensor(const b200seg_tensor* t) {
+  return t && t->ptr && t->n > 0 && t->d > 0 && t->h > 0 && t->w > 0 && t->c > 0 && t->ld >= t->c &&
+         (t->dtype == B200SEG_F32 || t->dtype == B200SEG_BF16);
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+#define ST(s) static_cast<cudaStream_t>(s)
+#define REQ_TENSOR(t, what) B200_CHECK_ARG(valid_tensor(t), "%s: invalid tensor descriptor '%s'", __func__, what)
+#define OPT_TENSOR(t, what) B200_CHECK_ARG((t) == nullptr || valid_tensor(t), "%s: invalid tensor descriptor '%s'", __func__, what)
+
+extern "C" {
+
+int b200seg_version(void) { return B200SEG_VERSION; }
+
+const char* b200seg_last_error(void) { return g_err; }
+
+int b200seg_init(int device) {
+  B200_DEVICE(device);
+  return conv_tc_init(device);
+}
+
+int b200seg_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N2, int N1, int64_t st, int64_t sk,
+                        int64_t sn2, int64_t sn1, int flip, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(w && out && T > 0 && K > 0 && N2 > 0 && N1 > 0, "b200seg_pack_weight: bad argument");
+  B200_CHECK_ARG(out_dtype == B200SEG_F32 || out_dtype == B200SEG_BF16, "b200seg_pack_weight: bad dtype");
+  B200_DEVICE(device);
+  return ew_pack_weight(w, out, out_dtype, T, K, N2, N1, st, sk, sn2, sn1, flip, ST(stream));
+}
+
+int b200seg_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, int64_t st, int64_t sk, int64_t sn,
+                         int device, b200seg_stream stream) {
+  B200_CHECK_ARG(dwp && grad && T > 0 && K > 0 && N > 0, "b200seg_unpack_wgrad: bad argument");
+  B200_DEVICE(device);
+  return ew_unpack_wgrad(dwp, grad, T, K, N, st, sk, sn, ST(stream));
+}
+
+int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, int w_dtype, const float* bias,
+                 const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device,
+                 b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  REQ_TENSOR(y, "y");
+  OPT_TENSOR(addend, "addend");
+  B200_CHECK_ARG(wpk != nullptr, "b200seg_conv: null weights");
+  B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_conv: dims must be 2 or 3");
+  B200_CHECK_ARG(dims == 3 || (x->d == 1 && y->d == 1), "b200seg_conv: 2-D tensors must have d == 1");
+  B200_DEVICE(device);
+  if (conv_tc_supported(kind, dims, x, w_dtype, y, addend))
+    return conv_tc(kind, dims, x, wpk, bias, y, stats, addend, device, ST(stream));
+  B200_CHECK_ARG(w_dtype != B200SEG_BF16_TC,
+                 "b200seg_conv: B200SEG_BF16_TC weights need bf16, 16-byte aligned activations of a supported shape");
+  return conv_generic(kind, dims, x, wpk, w_dtype, bias, y, stats, addend, ST(stream));
+}
+
+int b200seg_conv_tc_eligible(int kind, int cin, int cout) { return conv_tc_channels_ok(kind, cin, cout); }
+
+int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+                  b200seg_stream stream) {
+  REQ_TENSOR(a, "a");
+  REQ_TENSOR(b, "b");
+  B200_CHECK_ARG(dwp != nullptr, "b200seg_wgrad: null output");
+  B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_wgrad: dims must be 2 or 3");
+  B200_DEVICE(device);
+  return wgrad_generic(kind, dims, a, b, dwp, device, ST(stream));
+}
+
+int b200seg_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
+                        int groups, int64_t vox, float eps, float* coef, float* mr, int device,
+                        b200seg_stream stream) {
+  B200_CHECK_ARG(stats && gamma && beta && coef && mr && N > 0 && C > 0 && groups > 0 && vox > 0,
+                 "b200seg_gn_finalize: bad argument");
+  B200_DEVICE(device);
+  return ew_gn_finalize(stats, gamma, beta, scale, N, C, groups, vox, eps, coef, mr, ST(stream));
+}
+
+int b200seg_apply(const b200seg_tensor* y1, const float* coef1, const b200seg_tensor* y2, const float* coef2,
+                  const b200seg_tensor* res, const b200seg_tensor* out, int device, b200seg_stream stream) {
+  REQ_TENSOR(y1, "y1");
+  REQ_TENSOR(out, "out");
+  OPT_TENSOR(y2, "y2");
+  OPT_TENSOR(res, "res");
+  B200_CHECK_ARG(coef1 && (!y2 || coef2), "b200seg_apply: missing coefficients");
+  B200_DEVICE(device);
+  return ew_apply(y1, coef1, y2, coef2, res, out, device, ST(stream));
+}
+
+int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,
+                          b200seg_stream stream) {
+  REQ_TENSOR(g, "g");
+  REQ_TENSOR(y, "y");
+  B200_CHECK_ARG(coef && sums, "b200seg_gn_bwd_reduce: null argument");
+  B200_CHECK_ARG(y->c <= 4096, "b200seg_gn_bwd_reduce: too many channels");
+  B200_DEVICE(device);
+  return ew_gn_bwd_reduce(g, y, coef, sums, device, ST(stream));
+}
+
+int b200seg_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
+                            int groups, int64_t vox, float* coef3, float* dgamma, float* dbeta, float* dbias,
+                            int device, b200seg_stream stream) {
+  B200_CHECK_ARG(sums && mr && gamma && coef3 && dgamma && dbeta && N > 0 && C > 0 && groups > 0 && vox > 0,
+                 "b200seg_gn_bwd_finalize: bad argument");
+  B200_DEVICE(device);
+  return ew_gn_bwd_finalize(sums, mr, gamma, scale, N, C, groups, vox, coef3, dgamma, dbeta, dbias, ST(stream));
+}
+
+int b200seg_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
+                         const b200seg_tensor* dy, int device, b200seg_stream stream) {
+  REQ_TENSOR(g, "g");
+  REQ_TENSOR(y, "y");
+  REQ_TENSOR(dy, "dy");
+  B200_CHECK_ARG(coef && coef3, "b200seg_gn_bwd_apply: null coefficients");
+  B200_DEVICE(device);
+  return ew_gn_bwd_apply(g, y, coef, coef3, dy, device, ST(stream));
+}
+
+int b200seg_colsum(const b200seg_tensor* dy, float* out, int device, b200seg_stream stream) {
+  REQ_TENSOR(dy, "dy");
+  B200_CHECK_ARG(out != nullptr && dy->c <= 4096, "b200seg_colsum: bad argument");
+  B200_DEVICE(device);
+  return ew_colsum(dy, out, device, ST(stream));
+}
+
+int b200seg_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, int device, b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  REQ_TENSOR(out, "out");
+  B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_pool_fwd: dims must be 2 or 3");
+  B200_DEVICE(device);
+  return ew_pool_fwd(x, out, dims, device, ST(stream));
+}
+
+int b200seg_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* g_out, const b200seg_tensor* addend,
+                     const b200seg_tensor* g_x, int dims, int device, b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  REQ_TENSOR(g_out, "g_out");
+  REQ_TENSOR(g_x, "g_x");
+  OPT_TENSOR(addend, "addend");
+  B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_pool_bwd: dims must be 2 or 3");
+  B200_DEVICE(device);
+  return ew_pool_bwd(x, g_out, addend, g_x, dims, device, ST(stream));
+}
+
+int b200seg_head_probs(const float* logits, float* probs, int64_t nvox_, int C, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(logits && probs && nvox_ > 0 && C > 0, "b200seg_head_probs: bad argument");
+  B200_DEVICE(device);
+  return ew_head_probs(logits, probs, nvox_, C, device, ST(stream));
+}
+
+int b200seg_loss_partials(const float* logits, const int64_t* labels, int64_t nvox_, int C, float gamma, float alpha_f,
+                          double* part, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(logits && labels && part && nvox_ > 0, "b200seg_loss_partials: bad argument");
+  B200_DEVICE(device);
+  return loss_partials(logits, reinterpret_cast<const long long*>(labels), nvox_, C, gamma, alpha_f, part, device,
+                       ST(stream));
+}
+
+int b200seg_loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f,
+                          float* loss, float* lcoef, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(part && loss && lcoef && C >= 1 && (C == 1 || alpha), "b200seg_loss_finalize: bad argument");
+  B200_CHECK_ARG(terms > 0 && terms < 8, "b200seg_loss_finalize: bad terms mask %d", terms);
+  B200_DEVICE(device);
+  return loss_finalize(part, C, terms, alpha, gamma, alpha_f, loss, lcoef, ST(stream));
+}
+
+int b200seg_loss_bwd(const float* logits, const int64_t* labels, int64_t nvox_, int C, const float* lcoef,
+                     const float* gscale, float* dlogits, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(logits && labels && lcoef && gscale && dlogits && nvox_ > 0, "b200seg_loss_bwd: bad argument");
+  B200_DEVICE(device);
+  return loss_bwd(logits, reinterpret_cast<const long long*>(labels), nvox_, C, lcoef, gscale, dlogits, device,
+                  ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+// tcgen05 + TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Covers the dense-MMA-shaped members of the conv family in PERF mode: 3x3x3 / 3x3 (pad 1) and
+// 1x1x1 convolutions, forward and data-gradient form, Cin in {16, 32, 64k}, Cout = 16..256 (x16).
+//
+// GEMM view per CTA tile: M = 128 output voxels (a bw x bh x bd box of one sample), N = Cout,
+// K = taps x Cin.  One pipeline stage = one tap x one 16/32/64-channel block:
+//   A tile  : TMA 5-D tiled load of the NDHWC activation box shifted by the tap offset; the
+//             hardware zero-fills out-of-bounds voxels = the conv's zero padding; 128 rows of
+//             BKC*2 bytes land K-major with the 32/64/128-byte swizzle the UMMA descriptor names.
+//   B tile  : TMA 2-D load of the [tap*Cout + co][ci] packed weights (K-major, same swizzle).
+//   MMA     : one elected thread issues BKC/16 tcgen05.mma (M128 x N x K16) per stage into a TMEM
+//             accumulator; tcgen05.commit releases the smem stage / publishes the accumulator.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
+// epilogue (tcgen05.ld -> +bias -> GroupNorm sum/sumsq partials -> +addend -> bf16 NDHWC stores).
+// Two accumulator stages in TMEM overlap the epilogue of tile i with the main loop of tile i+1;
+// CTAs are persistent over contiguous tile ranges (grid = min(tiles, #SM)).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200seg {
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point (no -lcuda: resolved lazily so the library loads on machines without a driver)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int resolve_driver() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    set_error("cannot resolve cuTensorMapEncodeTiled from the CUDA driver");
+    return -1;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets TMEM lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, swizzled operand tile (rows of `swizzle_bytes`, 8-row atoms): SBO = 8 * swizzle_bytes
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t swizzle_bytes) {
+  const uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
+  const uint64_t sbo = (uint64_t)(8u * swizzle_bytes) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+  bf16* y;
+  const bf16* addend;
+  const float* bias;
+  double* stats;          // [N][Cout][2] or null
+  long long yld, ald;
+  int N, D, H, W;         // output (= input) spatial dims
+  int Cin, Cout;
+  int kd, kh, kw, pd, ph, pw;
+  int bw, bh, bd;         // M-tile box, bw*bh*bd == 128
+  int tw, th, td;         // tiles per dim
+  int ntiles;             // N * td * th * tw
+  int nstages;
+  int tmem_cols;          // power of two >= 2*Cout (>= 32)
+};
+
+constexpr int kMaxStages = 8;
+constexpr int kEpiWarps = 4;
+
+template <int BKC>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+  constexpr uint32_t SWZ = BKC * 2;                 // bytes per smem row = swizzle span
+  constexpr uint32_t A_BYTES = 128u * SWZ;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_bytes_real = (uint32_t)p.Cout * SWZ;
+  const uint32_t B_BYTES = (b_bytes_real + 1023u) & ~1023u;
+  const uint32_t STAGE = A_BYTES + B_BYTES;
+  uint8_t* tail = smem + (size_t)p.nstages * STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);     // [2][Cout]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_per_cta = (p.ntiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(p.ntiles, tile_begin + tiles_per_cta);
+  const int taps = p.kd * p.kh * p.kw;
+  const int cblocks = p.Cin / BKC;
+  const int kblocks = taps * cblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int t = tile;
+        const int iw = t % p.tw; t /= p.tw;
+        const int ih = t % p.th; t /= p.th;
+        const int id = t % p.td;
+        const int n = t / p.td;
+        const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kw_ = tap % p.kw;
+          const int kh_ = (tap / p.kw) % p.kh;
+          const int kd_ = tap / (p.kw * p.kh);
+          for (int cb = 0; cb < cblocks; ++cb, ++it) {
+            const uint32_t s = it % p.nstages;
+            const uint32_t ph = (it / p.nstages) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* sa = smem + (size_t)s * STAGE;
+            mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
+            tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
+            tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, tap * p.Cout);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t it = 0;
+    int local = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
+      const uint32_t as = local & 1;
+      const uint32_t aph = (local >> 1) & 1u;
+      mbar_wait(&tempty[as], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const uint32_t s = it % p.nstages;
+        const uint32_t ph = (it / p.nstages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
+          const uint64_t adesc = make_kmajor_desc(sa, SWZ);
+          const uint64_t bdesc = make_kmajor_desc(sa + A_BYTES, SWZ);
+#pragma unroll
+          for (int k = 0; k < BKC / 16; ++k) {
+            // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
+            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (2..5)
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // row of the M tile = voxel of the box
+    const int rw = row % p.bw;
+    const int rh = (row / p.bw) % p.bh;
+    const int rd = row / (p.bw * p.bh);
+    const int etid = threadIdx.x - 64;            // 0..127
+    int local = 0;
+    int cur_n = -1;
+    auto flush_stats = [&](int n) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.stats != nullptr && n >= 0) {
+        for (int i = etid; i < 2 * p.Cout; i += 128) {
+          const int which = i / p.Cout, c = i - which * p.Cout;
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, (double)s_stat[i]);
+          s_stat[i] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
+      int t = tile;
+      const int iw = t % p.tw; t /= p.tw;
+      const int ih = t % p.th; t /= p.th;
+      const int id = t % p.td;
+      const int n = t / p.td;
+      if (n != cur_n) {
+        if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
+        cur_n = n;
+      }
+      const int ow = iw * p.bw + rw, oh = ih * p.bh + rh, od = id * p.bd + rd;
+      const bool valid = ow < p.W && oh < p.H && od < p.D;
+      const long long vox = (((long long)n * p.D + od) * p.H + oh) * p.W + ow;
+      const uint32_t as = local & 1;
+      const uint32_t aph = (local >> 1) & 1u;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(tacc + (uint32_t)c0, v);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+        }
+        if (p.stats != nullptr) {
+          // butterfly transpose-reduce: after 5 steps lane L holds the warp total of column (L>>1)
+          float s[16], qq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s[j] = valid ? v[j] : 0.f;
+            qq[j] = s[j] * s[j];
+          }
+#pragma unroll
+          for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+              const float keep_s = up ? s[j + half] : s[j];
+              const float send_s = up ? s[j] : s[j + half];
+              const float keep_q = up ? qq[j + half] : qq[j];
+              const float send_q = up ? qq[j] : qq[j + half];
+              s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+          qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+          if ((lane & 1) == 0) {
+            // column owned by this lane: bit k of the index is bit (4-k) of the lane for k = 0..3
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            atomicAdd(&s_stat[c0 + col], s[0]);
+            atomicAdd(&s_stat[p.Cout + c0 + col], qq[0]);
+          }
+        }
+        if (valid) {
+          if (p.addend != nullptr) {
+            float r[16];
+            load8(p.addend + vox * p.ald + c0, r);
+            load8(p.addend + vox * p.ald + c0 + 8, r + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += r[j];
+          }
+          store8(p.y + vox * p.yld + c0, v);
+          store8(p.y + vox * p.yld + c0 + 8, v + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+    if (p.stats != nullptr && cur_n >= 0) flush_stats(cur_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
+
+static int pick_bkc(int cin) {
+  if (cin % 64 == 0) return 64;
+  if (cin == 32) return 32;
+  if (cin == 16) return 16;
+  return 0;
+}
+
+int conv_tc_channels_ok(int kind, int cin, int cout) {
+  if (kind != B200SEG_K3 && kind != B200SEG_K1) return 0;
+  if (pick_bkc(cin) == 0) return 0;
+  if (cout < 16 || cout > 256 || (cout % 16) != 0) return 0;
+  return 1;
+}
+
+int conv_tc_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                      const b200seg_tensor* addend) {
+  (void)dims;
+  if (w_dtype != B200SEG_BF16_TC) return 0;
+  if (!conv_tc_channels_ok(kind, x->c, y->c)) return 0;
+  if (x->dtype != B200SEG_BF16 || y->dtype != B200SEG_BF16) return 0;
+  if (addend && addend->dtype != B200SEG_BF16) return 0;
+  if ((x->ld % 8) || (y->ld % 8) || !al16p(x->ptr) || !al16p(y->ptr)) return 0;
+  if (addend && ((addend->ld % 8) || !al16p(addend->ptr))) return 0;
+  if (x->d != y->d || x->h != y->h || x->w != y->w) return 0;
+  return 1;
+}
+
+static void pick_box(int W, int H, int D, int* bw, int* bh, int* bd) {
+  long long best = -1;
+  int bb[3] = {16, 8, 1};
+  for (int w = 1; w <= 128; w *= 2)
+    for (int h = 1; w * h <= 128; h *= 2) {
+      int d = 128 / (w * h);
+      if (d > 128) continue;
+      long long padded = (long long)((W + w - 1) / w * w) * ((H + h - 1) / h * h) * ((D + d - 1) / d * d);
+      // prefer less padding, then wider rows (longer contiguous runs in memory)
+      long long score = padded * 1024 - w * 4 - h;
+      if (best < 0 || score < best) {
+        best = score;
+        bb[0] = w; bb[1] = h; bb[2] = d;
+      }
+    }
+  *bw = bb[0]; *bh = bb[1]; *bd = bb[2];
+}
+
+static int g_smem_optin[64] = {0};
+
+int conv_tc_init(int device) {
+  if (device < 0 || device >= 64) return B200SEG_OK;
+  if (g_smem_optin[device]) return B200SEG_OK;
+  int maxsm = 0;
+  B200_CUDA(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+  g_smem_optin[device] = maxsm;
+  return B200SEG_OK;
+}
+
+int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
+            double* stats, const b200seg_tensor* addend, int device, cudaStream_t st) {
+  if (resolve_driver() != 0) return B200SEG_ECUDA;
+  if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
+  ConvGeom g;
+  conv_geometry(kind, dims, &g);
+  TcArgs p;
+  p.y = static_cast<bf16*>(y->ptr);
+  p.addend = addend ? static_cast<const bf16*>(addend->ptr) : nullptr;
+  p.bias = bias;
+  p.stats = stats;
+  p.yld = y->ld;
+  p.ald = addend ? addend->ld : 0;
+  p.N = x->n; p.D = x->d; p.H = x->h; p.W = x->w;
+  p.Cin = x->c; p.Cout = y->c;
+  p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
+  pick_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd);
+  p.tw = (p.W + p.bw - 1) / p.bw;
+  p.th = (p.H + p.bh - 1) / p.bh;
+  p.td = (p.D + p.bd - 1) / p.bd;
+  p.ntiles = p.N * p.td * p.th * p.tw;
+  const int bkc = pick_bkc(p.Cin);
+  const uint32_t swz = bkc * 2;
+  const uint32_t a_bytes = 128u * swz;
+  const uint32_t b_bytes = (((uint32_t)p.Cout * swz) + 1023u) & ~1023u;
+  const uint32_t stage = a_bytes + b_bytes;
+  const uint32_t tail = (2 * kMaxStages + 4) * 8 + 16 + 2 * p.Cout * 4;
+  const int maxsm = g_smem_optin[device] > 0 ? g_smem_optin[device] : 227 * 1024;
+  int nst = (int)((maxsm - 1024 - (int)tail - 256) / (int)stage);
+  if (nst > kMaxStages) nst = kMaxStages;
+  B200_CHECK_ARG(nst >= 2, "conv_tc: tile does not fit in shared memory (Cin=%d Cout=%d)", p.Cin, p.Cout);
+  p.nstages = nst;
+  int cols = 32;
+  while (cols < 2 * p.Cout) cols *= 2;
+  p.tmem_cols = cols;
+  const size_t smem_bytes = 1024 + (size_t)nst * stage + tail + 128;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  const CUtensorMapSwizzle sw = bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : (bkc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  {
+    cuuint64_t dims5[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->ld * 2 * p.W, (cuuint64_t)x->ld * 2 * p.W * p.H,
+                             (cuuint64_t)x->ld * 2 * p.W * p.H * p.D};
+    cuuint32_t box[5] = {(cuuint32_t)bkc, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, dims5, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    const int taps = g.kd * g.kh * g.kw;
+    cuuint64_t dims2[2] = {(cuuint64_t)p.Cin, (cuuint64_t)taps * p.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bkc, (cuuint32_t)p.Cout};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpk), dims2, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  int grid = num_sms(device);
+  if (grid > p.ntiles) grid = p.ntiles;
+  if (bkc == 64) conv_tc_kernel<64><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
+  else if (bkc == 32) conv_tc_kernel<32><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
+  else conv_tc_kernel<16><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

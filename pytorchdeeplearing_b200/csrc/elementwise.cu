@@ -1,0 +1,637 @@
+// HBM-bound elementwise / reduction kernels of the hot path (sm_100a): weight (un)packing, the
+// GroupNorm finalize / apply split, GroupNorm+ReLU+Dropout backward (two-pass: per-(n,c) sums,
+// then dy = g*P + y*Q + R), bias column sums, 2x max-pooling, head sigmoid/softmax.
+//
+// All activation kernels use 128-bit accesses along the channel dimension of the NDHWC layout
+// (VEC = 8 bf16 / 4 fp32 channels per thread); the grid is sized so that a thread's channel group
+// never changes across its grid-stride loop, hence the per-(n,c) coefficients live in registers.
+#include "common.cuh"
+
+namespace b200seg {
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void pack_weight_kernel(const float* __restrict__ w, TO* __restrict__ out, int T, int K, int N2, int N1,
+                                   long long st, long long sk, long long sn2, long long sn1, int flip) {
+  long long total = (long long)T * K * N2 * N1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n1 = (int)(i % N1);
+    long long r = i / N1;
+    int n2 = (int)(r % N2);
+    r /= N2;
+    int k = (int)(r % K);
+    int t = (int)(r / K);
+    int ts = flip ? (T - 1 - t) : t;
+    out[i] = from_f<TO>(w[ts * st + k * sk + n2 * sn2 + n1 * sn1]);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int T, int K, int N,
+                                    long long st, long long sk, long long sn) {
+  // iterate in DESTINATION order when the destination's fastest index is t (st == 1): coalesced writes
+  long long total = (long long)T * K * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i % N);
+    long long r = i / N;
+    int k = (int)(r % K);
+    int t = (int)(r / K);
+    grad[t * st + k * sk + n * sn] = dwp[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm finalize: stats (double sum, sumsq per (n,c)) -> A,B per (n,c); mean,rstd per (n,g)
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ scale, int C, int groups,
+                                   double m, float eps, float* __restrict__ coef, float* __restrict__ mr) {
+  const int n = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cpg;
+    double s = 0.0, q = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      const double* p = stats + ((long long)n * C + g * cpg + j) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    double mean = s / m;
+    double var = q / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double rstd = rsqrt(var + (double)eps);
+    double sc = scale ? (double)scale[(long long)n * C + c] : 1.0;
+    double ga = gamma[c], be = beta[c];
+    coef[((long long)n * C + c) * 2 + 0] = (float)(rstd * ga * sc);
+    coef[((long long)n * C + c) * 2 + 1] = (float)((be - mean * rstd * ga) * sc);
+    if (c == g * cpg) {
+      mr[((long long)n * groups + g) * 2 + 0] = (float)mean;
+      mr[((long long)n * groups + g) * 2 + 1] = (float)rstd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector helpers: VEC channels of type T <-> float[VEC]
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC> struct Vec;
+template <> struct Vec<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float* o) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<bf16, 8> {
+  static __device__ __forceinline__ void load(const bf16* p, float* o) { load8(p, o); }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) { store8(p, v); }
+};
+template <typename T> struct Vec<T, 1> {
+  static __device__ __forceinline__ void load(const T* p, float* o) { o[0] = to_f(*p); }
+  static __device__ __forceinline__ void store(T* p, const float* v) { *p = from_f<T>(v[0]); }
+};
+
+// Common indexing: grid = (blocks, N); a thread walks "groups" (voxel, channel-group) of sample n with
+// stride gridDim.x*blockDim.x, which the host makes a multiple of G = C/VEC.
+#define EW_PROLOGUE(Cval)                                                        \
+  const int n = blockIdx.y;                                                      \
+  const int G = (Cval) / VEC;                                                    \
+  const long long total = V * G;                                                 \
+  const long long stride = (long long)gridDim.x * blockDim.x;                    \
+  long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x;               \
+  const int cg = (int)(gi % G);                                                  \
+  const int c0 = cg * VEC;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, long long ld1,
+                                                    const float* __restrict__ coef1, const T* __restrict__ y2,
+                                                    long long ld2, const float* __restrict__ coef2,
+                                                    const T* __restrict__ res, long long ldr, T* __restrict__ out,
+                                                    long long ldo, int C, long long V) {
+  EW_PROLOGUE(C)
+  float A1[VEC], B1[VEC], A2[VEC], B2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float* p = coef1 + ((long long)n * C + c0 + j) * 2;
+    A1[j] = p[0];
+    B1[j] = p[1];
+    if (y2 != nullptr) {
+      const float* q = coef2 + ((long long)n * C + c0 + j) * 2;
+      A2[j] = q[0];
+      B2[j] = q[1];
+    } else {
+      A2[j] = 0.f;
+      B2[j] = 0.f;
+    }
+  }
+  for (; gi < total; gi += stride) {
+    long long vox = (long long)n * V + gi / G;
+    float a[VEC], o[VEC];
+    Vec<T, VEC>::load(y1 + vox * ld1 + c0, a);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = fmaxf(fmaf(a[j], A1[j], B1[j]), 0.f);
+    if (y2 != nullptr) {
+      Vec<T, VEC>::load(y2 + vox * ld2 + c0, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] += fmaxf(fmaf(a[j], A2[j], B2[j]), 0.f);
+    }
+    if (res != nullptr) {
+      Vec<T, VEC>::load(res + vox * ldr + c0, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] += a[j];
+    }
+    Vec<T, VEC>::store(out + vox * ldo + c0, o);
+  }
+}
+
+// sums[n][c] += { sum g*m, sum g*m*y, sum y }, m = [y*A + B > 0]
+// The projection coefficients of the GroupNorm backward are means of these sums and their error is
+// amplified coherently over every voxel by the weight-gradient reduction, so the accumulation runs in
+// fp64 from the first add: fp64 per-thread partials -> shuffle across the lanes that share a channel
+// group -> low-contention fp64 shared atomics -> one fp64 global atomic per (channel, sum) per CTA.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict__ g, long long ldg,
+                                                            const T* __restrict__ y, long long ldy,
+                                                            const float* __restrict__ coef,
+                                                            double* __restrict__ sums, int C, long long V) {
+  EW_PROLOGUE(C)
+  extern __shared__ double s_redd[];   // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_redd[i] = 0.0;
+  __syncthreads();
+  float A[VEC], B[VEC];
+  double s1[VEC], s2[VEC], s3[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float* p = coef + ((long long)n * C + c0 + j) * 2;
+    A[j] = p[0];
+    B[j] = p[1];
+    s1[j] = s2[j] = s3[j] = 0.0;
+  }
+  for (; gi < total; gi += stride) {
+    long long vox = (long long)n * V + gi / G;
+    float yv[VEC], gv[VEC];
+    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
+    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] : 0.f;
+      s1[j] += (double)d;
+      s2[j] += (double)d * (double)yv[j];
+      s3[j] += (double)yv[j];
+    }
+  }
+  // lanes l and l ^ off share the channel group when off is a multiple of G (G a power of two <= 16)
+  const bool pow2 = (G & (G - 1)) == 0;
+  const int lane_groups = (pow2 && G < 32) ? G : 32;
+  if (lane_groups < 32) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      for (int off = 16; off >= lane_groups; off >>= 1) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+        s3[j] += __shfl_xor_sync(0xffffffffu, s3[j], off);
+      }
+    }
+  }
+  if ((int)(threadIdx.x & 31) < lane_groups) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      atomicAdd(&s_redd[0 * C + c0 + j], s1[j]);
+      atomicAdd(&s_redd[1 * C + c0 + j], s2[j]);
+      atomicAdd(&s_redd[2 * C + c0 + j], s3[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    int k = i / C, c = i - k * C;
+    atomicAdd(sums + ((long long)n * C + c) * 3 + k, s_redd[i]);
+  }
+}
+
+// one block; thread per channel.  See SURVEY.md App. G for the algebra.
+__global__ void gn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ mr,
+                                       const float* __restrict__ gamma, const float* __restrict__ scale, int N, int C,
+                                       int groups, double vox, float* __restrict__ coef3,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ dbias) {
+  const int cpg = C / groups;
+  const double m = (double)cpg * vox;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const int g = c / cpg;
+    double dg = 0.0, db = 0.0, dbi = 0.0;
+    const double ga = gamma[c];
+    for (int n = 0; n < N; ++n) {
+      const double mu = mr[((long long)n * groups + g) * 2 + 0];
+      const double r = mr[((long long)n * groups + g) * 2 + 1];
+      double sa = 0.0, sax = 0.0;
+      for (int j = 0; j < cpg; ++j) {
+        const int cj = g * cpg + j;
+        const double sj = scale ? (double)scale[(long long)n * C + cj] : 1.0;
+        const double* p = sums + ((long long)n * C + cj) * 3;
+        const double s1 = p[0] * sj, s2 = p[1] * sj;
+        const double gj = gamma[cj];
+        sa += gj * s1;
+        sax += gj * r * (s2 - mu * s1);
+      }
+      const double m1 = sa / m, m2 = sax / m;
+      const double sc = scale ? (double)scale[(long long)n * C + c] : 1.0;
+      const double* p = sums + ((long long)n * C + c) * 3;
+      const double s1 = p[0] * sc, s2 = p[1] * sc, s3 = p[2];
+      const double P = r * ga * sc;
+      const double Q = -r * r * m2;
+      const double R = -r * m1 + r * r * mu * m2;
+      float* o = coef3 + ((long long)n * C + c) * 3;
+      o[0] = (float)P;
+      o[1] = (float)Q;
+      o[2] = (float)R;
+      db += s1;
+      dg += r * (s2 - mu * s1);
+      dbi += r * ga * s1 + Q * s3 + R * vox;
+    }
+    dgamma[c] += (float)dg;
+    dbeta[c] += (float)db;
+    if (dbias != nullptr) dbias[c] = (float)dbi;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__ g, long long ldg,
+                                                           const T* __restrict__ y, long long ldy,
+                                                           const float* __restrict__ coef,
+                                                           const float* __restrict__ coef3, T* __restrict__ dy,
+                                                           long long ldd, int C, long long V) {
+  EW_PROLOGUE(C)
+  float A[VEC], B[VEC], P[VEC], Q[VEC], R[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float* p = coef + ((long long)n * C + c0 + j) * 2;
+    A[j] = p[0];
+    B[j] = p[1];
+    const float* q = coef3 + ((long long)n * C + c0 + j) * 3;
+    P[j] = q[0];
+    Q[j] = q[1];
+    R[j] = q[2];
+  }
+  for (; gi < total; gi += stride) {
+    long long vox = (long long)n * V + gi / G;
+    float yv[VEC], gv[VEC], o[VEC];
+    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
+    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] * P[j] : 0.f;
+      o[j] = d + fmaf(yv[j], Q[j], R[j]);
+    }
+    Vec<T, VEC>::store(dy + vox * ldd + c0, o);
+  }
+}
+
+// out[c] += sum over all voxels of all samples
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
+                                                     int C, long long V) {
+  EW_PROLOGUE(C)
+  extern __shared__ float s_red[];   // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  float s[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] = 0.f;
+  for (; gi < total; gi += stride) {
+    long long vox = (long long)n * V + gi / G;
+    float v[VEC];
+    Vec<T, VEC>::load(x + vox * ld + c0, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) atomicAdd(&s_red[c0 + j], s[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, s_red[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x max pooling (window kd x 2 x 2, kd = 2 for 3-D, 1 for 2-D)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out,
+                                                       long long ldo, int C, int OD, int OH, int OW, int kd) {
+  const long long V = (long long)OD * OH * OW;
+  EW_PROLOGUE(C)
+  const int XH = OH * 2, XW = OW * 2, XD = OD * kd;
+  for (; gi < total; gi += stride) {
+    long long o = gi / G;
+    int ow = (int)(o % OW);
+    long long t2 = o / OW;
+    int oh = (int)(t2 % OH);
+    int od = (int)(t2 / OH);
+    float best[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) best[j] = -INFINITY;
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          long long vox = (((long long)n * XD + od * kd + a) * XH + oh * 2 + b) * XW + ow * 2 + c;
+          float v[VEC];
+          Vec<T, VEC>::load(x + vox * ldx + c0, v);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) best[j] = fmaxf(best[j], v[j]);
+        }
+    Vec<T, VEC>::store(out + ((long long)n * V + o) * ldo + c0, best);
+  }
+}
+
+// thread per (coarse voxel, channel group): g_x[window] = addend[window] + (first arg-max ? g_out : 0)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ x, long long ldx,
+                                                       const T* __restrict__ go, long long ldg,
+                                                       const T* __restrict__ addend, long long lda,
+                                                       T* __restrict__ gx, long long ldo, int C, int OD, int OH,
+                                                       int OW, int kd) {
+  const long long V = (long long)OD * OH * OW;
+  EW_PROLOGUE(C)
+  const int XH = OH * 2, XW = OW * 2, XD = OD * kd;
+  for (; gi < total; gi += stride) {
+    long long o = gi / G;
+    int ow = (int)(o % OW);
+    long long t2 = o / OW;
+    int oh = (int)(t2 % OH);
+    int od = (int)(t2 / OH);
+    float best[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      best[j] = -INFINITY;
+      arg[j] = 0;
+    }
+    int widx = 0;
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c, ++widx) {
+          long long vox = (((long long)n * XD + od * kd + a) * XH + oh * 2 + b) * XW + ow * 2 + c;
+          float v[VEC];
+          Vec<T, VEC>::load(x + vox * ldx + c0, v);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (v[j] > best[j]) {
+              best[j] = v[j];
+              arg[j] = widx;
+            }
+        }
+    float gv[VEC];
+    Vec<T, VEC>::load(go + ((long long)n * V + o) * ldg + c0, gv);
+    widx = 0;
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c, ++widx) {
+          long long vox = (((long long)n * XD + od * kd + a) * XH + oh * 2 + b) * XW + ow * 2 + c;
+          float r[VEC];
+          if (addend != nullptr) {
+            Vec<T, VEC>::load(addend + vox * lda + c0, r);
+          } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) r[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (arg[j] == widx) r[j] += gv[j];
+          Vec<T, VEC>::store(gx + vox * ldo + c0, r);
+        }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// head: sigmoid (C == 1) / softmax over channels (C > 1), fp32 channels-last
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_probs_kernel(const float* __restrict__ z, float* __restrict__ p,
+                                                         long long nvox, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* zi = z + i * C;
+    float* pi = p + i * C;
+    if (C == 1) {
+      pi[0] = 1.f / (1.f + expf(-zi[0]));
+    } else if (C == 2) {
+      float2 v = *reinterpret_cast<const float2*>(zi);
+      float mx = fmaxf(v.x, v.y);
+      float e0 = expf(v.x - mx), e1 = expf(v.y - mx);
+      float inv = 1.f / (e0 + e1);
+      *reinterpret_cast<float2*>(pi) = make_float2(e0 * inv, e1 * inv);
+    } else {
+      float mx = zi[0];
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, zi[c]);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += expf(zi[c] - mx);
+      float inv = 1.f / s;
+      for (int c = 0; c < C; ++c) pi[c] = expf(zi[c] - mx) * inv;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ---------------------------------------------------------------------------------------------
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
+
+// can tensor t be accessed with 16-byte channel vectors?
+static bool vec_ok(const b200seg_tensor* t) {
+  if (t == nullptr) return true;
+  const int vec = t->dtype == B200SEG_BF16 ? 8 : 4;
+  return (t->c % vec == 0) && (t->ld % vec == 0) && al16(t->ptr);
+}
+
+// blocks per sample such that gridDim.x*256 is a multiple of G and the grid fills the chip
+static int ew_blocks(long long V, int G, int N, int device) {
+  long long total = V * G;
+  long long want = (total + 256 * 4 - 1) / (256 * 4);        // ~4 groups per thread
+  long long cap = ((long long)num_sms(device) * 8 + N - 1) / N;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  // 256 % G == 0 for every power-of-two G <= 256; otherwise round blocks so that blocks*256 % G == 0
+  if (256 % G != 0) {
+    long long k = G;   // blocks multiple of G always works
+    want = ((want + k - 1) / k) * k;
+  }
+  return (int)want;
+}
+
+#define EW_DISPATCH(TENSOR_FOR_DTYPE, ALL_VEC_OK, ...)                          \
+  do {                                                                           \
+    if ((TENSOR_FOR_DTYPE)->dtype == B200SEG_BF16) {                             \
+      typedef bf16 T;                                                            \
+      if (ALL_VEC_OK) { constexpr int VEC = 8; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; } \
+    } else {                                                                     \
+      typedef float T;                                                           \
+      if (ALL_VEC_OK) { constexpr int VEC = 4; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; } \
+    }                                                                            \
+  } while (0)
+
+int ew_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N2, int N1, long long st,
+                   long long sk, long long sn2, long long sn1, int flip, cudaStream_t s) {
+  long long total = (long long)T * K * N2 * N1;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  if (blocks < 1) blocks = 1;
+  if (out_dtype == B200SEG_BF16)
+    pack_weight_kernel<bf16><<<blocks, 256, 0, s>>>(w, static_cast<bf16*>(out), T, K, N2, N1, st, sk, sn2, sn1, flip);
+  else
+    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, static_cast<float*>(out), T, K, N2, N1, st, sk, sn2, sn1, flip);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, long long st, long long sk, long long sn,
+                    cudaStream_t s) {
+  long long total = (long long)T * K * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  if (blocks < 1) blocks = 1;
+  unpack_wgrad_kernel<<<blocks, 256, 0, s>>>(dwp, grad, T, K, N, st, sk, sn);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
+                   int groups, long long vox, float eps, float* coef, float* mr, cudaStream_t s) {
+  B200_CHECK_ARG(C % groups == 0, "gn_finalize: C=%d not divisible by groups=%d", C, groups);
+  double m = (double)(C / groups) * (double)vox;
+  gn_finalize_kernel<<<N, 256, 0, s>>>(stats, gamma, beta, scale, C, groups, m, eps, coef, mr);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_tensor* y2, const float* c2,
+             const b200seg_tensor* res, const b200seg_tensor* out, int device, cudaStream_t s) {
+  B200_CHECK_ARG(same_geom(y1, out) && (!y2 || same_geom(y2, out)) && (!res || same_geom(res, out)),
+                 "apply: shape mismatch");
+  B200_CHECK_ARG(y1->dtype == out->dtype && (!y2 || y2->dtype == out->dtype) && (!res || res->dtype == out->dtype),
+                 "apply: dtype mismatch");
+  const bool vok = vec_ok(y1) && vec_ok(y2) && vec_ok(res) && vec_ok(out);
+  const long long V = nvox(out);
+  const int C = out->c;
+  EW_DISPATCH(out, vok, {
+    const int G = C / VEC;
+    dim3 grid(ew_blocks(V, G, out->n, device), out->n);
+    apply_kernel<T, VEC><<<grid, 256, 0, s>>>(
+        static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
+        res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,
+                     cudaStream_t s) {
+  B200_CHECK_ARG(same_geom(g, y) && g->dtype == y->dtype, "gn_bwd_reduce: g/y mismatch");
+  const bool vok = vec_ok(g) && vec_ok(y);
+  const long long V = nvox(y);
+  const int C = y->c;
+  EW_DISPATCH(y, vok, {
+    const int G = C / VEC;
+    dim3 grid(ew_blocks(V, G, y->n, device), y->n);
+    gn_bwd_reduce_kernel<T, VEC><<<grid, 256, 3 * C * sizeof(double), s>>>(
+        static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
+                       int groups, long long vox, float* coef3, float* dgamma, float* dbeta, float* dbias,
+                       cudaStream_t s) {
+  B200_CHECK_ARG(C % groups == 0, "gn_bwd_finalize: C=%d not divisible by groups=%d", C, groups);
+  int blocks = (C + 63) / 64;
+  gn_bwd_finalize_kernel<<<blocks, 64, 0, s>>>(sums, mr, gamma, scale, N, C, groups, (double)vox, coef3, dgamma,
+                                               dbeta, dbias);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
+                    const b200seg_tensor* dy, int device, cudaStream_t s) {
+  B200_CHECK_ARG(same_geom(g, y) && same_geom(dy, y) && g->dtype == y->dtype && dy->dtype == y->dtype,
+                 "gn_bwd_apply: tensor mismatch");
+  const bool vok = vec_ok(g) && vec_ok(y) && vec_ok(dy);
+  const long long V = nvox(y);
+  const int C = y->c;
+  EW_DISPATCH(y, vok, {
+    const int G = C / VEC;
+    dim3 grid(ew_blocks(V, G, y->n, device), y->n);
+    gn_bwd_apply_kernel<T, VEC><<<grid, 256, 0, s>>>(static_cast<const T*>(g->ptr), g->ld,
+                                                     static_cast<const T*>(y->ptr), y->ld, coef, coef3,
+                                                     static_cast<T*>(dy->ptr), dy->ld, C, V);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_colsum(const b200seg_tensor* dy, float* out, int device, cudaStream_t s) {
+  const bool vok = vec_ok(dy);
+  const long long V = nvox(dy);
+  const int C = dy->c;
+  EW_DISPATCH(dy, vok, {
+    const int G = C / VEC;
+    dim3 grid(ew_blocks(V, G, dy->n, device), dy->n);
+    colsum_kernel<T, VEC><<<grid, 256, C * sizeof(float), s>>>(static_cast<const T*>(dy->ptr), dy->ld, out, C, V);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, int device, cudaStream_t s) {
+  const int kd = dims == 3 ? 2 : 1;
+  B200_CHECK_ARG(x->n == out->n && x->c == out->c && x->d == out->d * kd && x->h == out->h * 2 &&
+                     x->w == out->w * 2 && x->dtype == out->dtype,
+                 "pool_fwd: shape mismatch");
+  const bool vok = vec_ok(x) && vec_ok(out);
+  const long long V = nvox(out);
+  const int C = out->c;
+  EW_DISPATCH(out, vok, {
+    const int G = C / VEC;
+    dim3 grid(ew_blocks(V, G, out->n, device), out->n);
+    pool_fwd_kernel<T, VEC><<<grid, 256, 0, s>>>(static_cast<const T*>(x->ptr), x->ld, static_cast<T*>(out->ptr),
+                                                 out->ld, C, out->d, out->h, out->w, kd);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* go, const b200seg_tensor* addend,
+                const b200seg_tensor* gx, int dims, int device, cudaStream_t s) {
+  const int kd = dims == 3 ? 2 : 1;
+  B200_CHECK_ARG(same_geom(x, gx) && (!addend || same_geom(addend, gx)) && x->n == go->n && x->c == go->c &&
+                     x->d == go->d * kd && x->h == go->h * 2 && x->w == go->w * 2,
+                 "pool_bwd: shape mismatch");
+  B200_CHECK_ARG(x->dtype == gx->dtype && go->dtype == gx->dtype && (!addend || addend->dtype == gx->dtype),
+                 "pool_bwd: dtype mismatch");
+  const bool vok = vec_ok(x) && vec_ok(go) && vec_ok(addend) && vec_ok(gx);
+  const long long V = nvox(go);
+  const int C = go->c;
+  EW_DISPATCH(gx, vok, {
+    const int G = C / VEC;
+    dim3 grid(ew_blocks(V, G, go->n, device), go->n);
+    pool_bwd_kernel<T, VEC><<<grid, 256, 0, s>>>(
+        static_cast<const T*>(x->ptr), x->ld, static_cast<const T*>(go->ptr), go->ld,
+        addend ? static_cast<const T*>(addend->ptr) : nullptr, addend ? addend->ld : 0, static_cast<T*>(gx->ptr),
+        gx->ld, C, go->d, go->h, go->w, kd);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int ew_head_probs(const float* logits, float* probs, long long nvox_, int C, int device, cudaStream_t s) {
+  long long blocks = (nvox_ + 255) / 256;
+  long long cap = (long long)num_sms(device) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  head_probs_kernel<<<(int)blocks, 256, 0, s>>>(logits, probs, nvox_, C);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

@@ -1,0 +1,379 @@
+// Fused segmentation losses (sm_100a): ONE reduction pass over logits + labels producing every
+// partial sum the Dice / BCE / CE / focal family needs, a scalar finalize, and ONE elementwise
+// backward pass writing d loss / d logits (closed forms: SURVEY.md App. C; reference formulas:
+// model/losses.py:43-53,141-147,160-181,252-260,273-285,301-325).
+// logits: fp32 channels-last [nvox][C]; labels: int64 [nvox] (read as-is, 8 B/voxel).
+#include "common.cuh"
+
+namespace b200seg {
+
+
+__device__ __forceinline__ double block_reduce_to_global(double v, double* dst, double* s_tmp) {
+  // warp shuffle -> one smem slot per warp -> thread 0 adds to global
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_tmp[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_tmp[i];
+    atomicAdd(dst, t);
+  }
+  __syncthreads();
+  return v;
+}
+
+__device__ __forceinline__ float softplus_neg_abs(float z) { return log1pf(expf(-fabsf(z))); }
+
+// ---- binary (C == 1): I = sum p t, P = sum p, T = sum t, sum bce, sum alpha (1-pt)^gamma bce, V
+__global__ void __launch_bounds__(256) loss_partials_binary_kernel(const float* __restrict__ z,
+                                                                   const long long* __restrict__ t, long long nvox,
+                                                                   float gamma, float alpha_f,
+                                                                   double* __restrict__ part) {
+  __shared__ double s_tmp[8];
+  float aI = 0.f, aP = 0.f, aT = 0.f, aB = 0.f, aF = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    float zi = z[i];
+    float ti = (float)t[i];
+    float p = 1.f / (1.f + expf(-zi));
+    float b = fmaxf(zi, 0.f) - zi * ti + softplus_neg_abs(zi);
+    float pt = expf(-b);
+    aI = fmaf(p, ti, aI);
+    aP += p;
+    aT += ti;
+    aB += b;
+    aF += alpha_f * powf(1.f - pt, gamma) * b;
+  }
+  block_reduce_to_global((double)aI, part + 0, s_tmp);
+  block_reduce_to_global((double)aP, part + 1, s_tmp);
+  block_reduce_to_global((double)aT, part + 2, s_tmp);
+  block_reduce_to_global((double)aB, part + 3, s_tmp);
+  block_reduce_to_global((double)aF, part + 4, s_tmp);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 5, (double)nvox);
+}
+
+// ---- multi-class, C <= kMaxC in registers
+template <int C>
+__global__ void __launch_bounds__(256) loss_partials_multi_kernel(const float* __restrict__ z,
+                                                                  const long long* __restrict__ t, long long nvox,
+                                                                  float gamma, double* __restrict__ part) {
+  __shared__ double s_tmp[8];
+  float aI[C], aP[C], aN[C];
+  float aNll = 0.f, aF = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) aI[c] = aP[c] = aN[c] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[C];
+    if (C == 2) {
+      float2 q = *reinterpret_cast<const float2*>(z + i * 2);
+      v[0] = q.x; v[1] = q.y;
+    } else if (C == 4) {
+      float4 q = *reinterpret_cast<const float4*>(z + i * 4);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = z[i * C + c];
+    }
+    const int ti = (int)t[i];
+    float mx = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c]);
+    float s = 0.f, e[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      e[c] = expf(v[c] - mx);
+      s += e[c];
+    }
+    const float inv = 1.f / s;
+    const float lse = mx + logf(s);
+    float zt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float p = e[c] * inv;
+      const bool hit = (c == ti);
+      aP[c] += p;
+      if (hit) {
+        aI[c] += p;
+        aN[c] += 1.f;
+        zt = v[c];
+      }
+    }
+    const float nll = lse - zt;
+    const float ptt = expf(-nll);
+    aNll += nll;
+    aF += powf(1.f - ptt, gamma) * nll;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    block_reduce_to_global((double)aI[c], part + c, s_tmp);
+    block_reduce_to_global((double)aP[c], part + C + c, s_tmp);
+    block_reduce_to_global((double)aN[c], part + 2 * C + c, s_tmp);
+  }
+  block_reduce_to_global((double)aNll, part + 3 * C, s_tmp);
+  block_reduce_to_global((double)aF, part + 3 * C + 1, s_tmp);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 3 * C + 2, (double)nvox);
+}
+
+// ---- multi-class, any C (<= 1024): per-class sums through shared-memory atomics
+__global__ void __launch_bounds__(256) loss_partials_multi_generic_kernel(const float* __restrict__ z,
+                                                                          const long long* __restrict__ t,
+                                                                          long long nvox, int C, float gamma,
+                                                                          double* __restrict__ part) {
+  extern __shared__ float s_acc[];   // [3*C + 2]
+  for (int i = threadIdx.x; i < 3 * C + 2; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* zi = z + i * C;
+    const int ti = (int)t[i];
+    float mx = zi[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, zi[c]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(zi[c] - mx);
+    const float inv = 1.f / s, lse = mx + logf(s);
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(zi[c] - mx) * inv;
+      atomicAdd(&s_acc[C + c], p);
+      if (c == ti) {
+        atomicAdd(&s_acc[c], p);
+        atomicAdd(&s_acc[2 * C + c], 1.f);
+      }
+    }
+    const float nll = lse - zi[ti];
+    atomicAdd(&s_acc[3 * C], nll);
+    atomicAdd(&s_acc[3 * C + 1], powf(1.f - expf(-nll), gamma) * nll);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C + 2; i += blockDim.x) atomicAdd(part + i, (double)s_acc[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 3 * C + 2, (double)nvox);
+}
+
+// ---- finalize: one thread
+__global__ void loss_finalize_kernel(const double* __restrict__ part, int C, int terms,
+                                     const float* __restrict__ alpha, float gamma, float alpha_f,
+                                     float* __restrict__ loss, float* __restrict__ lcoef) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double s = 1e-5, eps = 1e-7;
+  double val = 0.0;
+  if (C == 1) {
+    const double I = part[0], P = part[1], T = part[2], sb = part[3], sf = part[4], V = part[5];
+    double a = 0.0, b = 0.0;
+    const double den = P + T + s;
+    if (terms & B200SEG_LOSS_DICE) {
+      const double dcl = den < eps ? eps : den;
+      val += 1.0 - (2.0 * I + s) / dcl;
+      a = -2.0 / den;
+      b = (2.0 * I + s) / (den * den);
+    }
+    if (terms & B200SEG_LOSS_CE) val += sb / V;
+    if (terms & B200SEG_LOSS_FOCAL) val += sf / V;
+    lcoef[0] = (float)a;
+    lcoef[1] = (float)b;
+    lcoef[2] = (terms & B200SEG_LOSS_CE) ? (float)(1.0 / V) : 0.f;
+    lcoef[3] = (terms & B200SEG_LOSS_FOCAL) ? (float)((double)alpha_f / V) : 0.f;
+    lcoef[4] = gamma;
+  } else {
+    const double* I = part;
+    const double* Ps = part + C;
+    const double* Cn = part + 2 * C;
+    const double snll = part[3 * C], sfoc = part[3 * C + 1], V = part[3 * C + 2];
+    double K = 0.0;
+    for (int c = 0; c < C; ++c) K += Cn[c] > 0.0 ? 1.0 : 0.0;
+    for (int c = 0; c < C; ++c) {
+      double a = 0.0, b = 0.0;
+      if (terms & B200SEG_LOSS_DICE) {
+        const double present = Cn[c] > 0.0 ? 1.0 : 0.0;
+        const double D = Cn[c] + Ps[c];
+        const double draw = (2.0 * I[c] + s) / (D + s);
+        const double d = draw < eps ? eps : draw;
+        const double al = alpha[c];
+        val += -(d * present * al) / K;
+        const double w = (draw >= eps) ? al * present / K : 0.0;
+        a = -2.0 * w / (D + s);
+        b = w * (2.0 * I[c] + s) / ((D + s) * (D + s));
+      }
+      lcoef[c] = (float)a;
+      lcoef[C + c] = (float)b;
+    }
+    if (terms & B200SEG_LOSS_CE) val += snll / V;
+    if (terms & B200SEG_LOSS_FOCAL) val += sfoc / V;
+    lcoef[2 * C] = (terms & B200SEG_LOSS_CE) ? (float)(1.0 / V) : 0.f;
+    lcoef[2 * C + 1] = (terms & B200SEG_LOSS_FOCAL) ? (float)(1.0 / V) : 0.f;
+    lcoef[2 * C + 2] = gamma;
+  }
+  loss[0] = (float)val;
+}
+
+// d/dce of (1-pt)^gamma * ce with pt = exp(-ce):  (1-pt)^gamma + gamma (1-pt)^(gamma-1) pt ce
+__device__ __forceinline__ float focal_factor(float ce, float gamma) {
+  const float pt = expf(-ce);
+  const float om = 1.f - pt;
+  if (gamma == 2.f) return om * om + 2.f * om * pt * ce;
+  if (om <= 0.f) return gamma == 1.f ? pt * ce : 0.f;
+  return powf(om, gamma) + gamma * powf(om, gamma - 1.f) * pt * ce;
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_binary_kernel(const float* __restrict__ z,
+                                                              const long long* __restrict__ t, long long nvox,
+                                                              const float* __restrict__ lcoef,
+                                                              const float* __restrict__ gscale,
+                                                              float* __restrict__ dz) {
+  const float a = lcoef[0], b = lcoef[1], cs = lcoef[2], fs = lcoef[3], gamma = lcoef[4];
+  const float gs = gscale[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float zi = z[i];
+    const float ti = (float)t[i];
+    const float p = 1.f / (1.f + expf(-zi));
+    float g = (ti * a + b) * p * (1.f - p) + cs * (p - ti);
+    if (fs != 0.f) {
+      const float bce = fmaxf(zi, 0.f) - zi * ti + softplus_neg_abs(zi);
+      g += fs * focal_factor(bce, gamma) * (p - ti);
+    }
+    dz[i] = g * gs;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) loss_bwd_multi_kernel(const float* __restrict__ z,
+                                                             const long long* __restrict__ t, long long nvox,
+                                                             const float* __restrict__ lcoef,
+                                                             const float* __restrict__ gscale,
+                                                             float* __restrict__ dz) {
+  float a[C], b[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    a[c] = lcoef[c];
+    b[c] = lcoef[C + c];
+  }
+  const float cs = lcoef[2 * C], fs = lcoef[2 * C + 1], gamma = lcoef[2 * C + 2];
+  const float gs = gscale[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[C], p[C], o[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = z[i * C + c];
+    const int ti = (int)t[i];
+    float mx = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      p[c] = expf(v[c] - mx);
+      s += p[c];
+    }
+    const float inv = 1.f / s;
+    float dot = 0.f, zt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      p[c] *= inv;
+      const float gd = (c == ti ? a[c] : 0.f) + b[c];
+      o[c] = gd;
+      dot = fmaf(gd, p[c], dot);
+      if (c == ti) zt = v[c];
+    }
+    float k = cs;
+    if (fs != 0.f) {
+      const float nll = mx + logf(s) - zt;
+      k += fs * focal_factor(nll, gamma);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float oh = (c == ti) ? 1.f : 0.f;
+      dz[i * C + c] = (p[c] * (o[c] - dot) + k * (p[c] - oh)) * gs;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_multi_generic_kernel(const float* __restrict__ z,
+                                                                     const long long* __restrict__ t,
+                                                                     long long nvox, int C,
+                                                                     const float* __restrict__ lcoef,
+                                                                     const float* __restrict__ gscale,
+                                                                     float* __restrict__ dz) {
+  const float cs = lcoef[2 * C], fs = lcoef[2 * C + 1], gamma = lcoef[2 * C + 2];
+  const float gs = gscale[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* zi = z + i * C;
+    const int ti = (int)t[i];
+    float mx = zi[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, zi[c]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(zi[c] - mx);
+    const float inv = 1.f / s;
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(zi[c] - mx) * inv;
+      dot = fmaf((c == ti ? lcoef[c] : 0.f) + lcoef[C + c], p, dot);
+    }
+    float k = cs;
+    if (fs != 0.f) k += fs * focal_factor(mx + logf(s) - zi[ti], gamma);
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(zi[c] - mx) * inv;
+      const float gd = (c == ti ? lcoef[c] : 0.f) + lcoef[C + c];
+      dz[i * C + c] = (p * (gd - dot) + k * (p - (c == ti ? 1.f : 0.f))) * gs;
+    }
+  }
+}
+
+static int loss_blocks(long long nvox_, int device) {
+  long long blocks = (nvox_ + 256 * 4 - 1) / (256 * 4);
+  long long cap = (long long)num_sms(device) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int loss_partials(const float* logits, const long long* labels, long long nvox_, int C, float gamma, float alpha_f,
+                  double* part, int device, cudaStream_t s) {
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "loss_partials: unsupported class count %d", C);
+  const int blocks = loss_blocks(nvox_, device);
+  switch (C) {
+    case 1: loss_partials_binary_kernel<<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, alpha_f, part); break;
+    case 2: loss_partials_multi_kernel<2><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 3: loss_partials_multi_kernel<3><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 4: loss_partials_multi_kernel<4><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 5: loss_partials_multi_kernel<5><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 6: loss_partials_multi_kernel<6><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 7: loss_partials_multi_kernel<7><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 8: loss_partials_multi_kernel<8><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    default:
+      loss_partials_multi_generic_kernel<<<blocks, 256, (3 * C + 2) * sizeof(float), s>>>(logits, labels, nvox_, C,
+                                                                                          gamma, part);
+  }
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f, float* loss,
+                  float* lcoef, cudaStream_t s) {
+  loss_finalize_kernel<<<1, 32, 0, s>>>(part, C, terms, alpha, gamma, alpha_f, loss, lcoef);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int loss_bwd(const float* logits, const long long* labels, long long nvox_, int C, const float* lcoef,
+             const float* gscale, float* dlogits, int device, cudaStream_t s) {
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "loss_bwd: unsupported class count %d", C);
+  const int blocks = loss_blocks(nvox_, device);
+  switch (C) {
+    case 1: loss_bwd_binary_kernel<<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 2: loss_bwd_multi_kernel<2><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 3: loss_bwd_multi_kernel<3><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 4: loss_bwd_multi_kernel<4><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 5: loss_bwd_multi_kernel<5><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 6: loss_bwd_multi_kernel<6><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 7: loss_bwd_multi_kernel<7><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 8: loss_bwd_multi_kernel<8><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    default:
+      loss_bwd_multi_generic_kernel<<<blocks, 256, 0, s>>>(logits, labels, nvox_, C, lcoef, gscale, dlogits);
+  }
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

@@ -1,0 +1,273 @@
+"""Per-entry-point parity of the sm_100a kernels (through the C ABI) against the test-only
+PyTorch statement of the same op (tests/emu_backend.py, CPU fp32/fp64).  `-m gpu`."""
+import pytest
+import torch
+
+from emu_backend import EmuBackend, K3, K1, DOWN, UP
+
+pytestmark = pytest.mark.gpu
+
+EMU = EmuBackend()
+
+
+@pytest.fixture(scope="module")
+def be():
+    from pytorchdeeplearing_b200._abi import CudaBackend
+    return CudaBackend()
+
+
+def dev(t):
+    return None if t is None else t.cuda()
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def tol(dtype, k=1.0):
+    return (3e-5 if dtype == torch.float32 else 1.2e-2) * k
+
+
+def rnd(shape, dtype, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+def sliced(n, sp, c, dtype, g, pad):
+    """activation view with channel pitch > C when pad"""
+    if pad:
+        full = rnd((n,) + sp + (c + pad,), dtype, g)
+        return full[..., pad // 2: pad // 2 + c]
+    return rnd((n,) + sp + (c,), dtype, g)
+
+
+CONV_CASES = [
+    # kind, dims, n, in-spatial, cin, cout
+    (K3, 3, 2, (6, 10, 12), 16, 16),
+    (K3, 3, 1, (5, 7, 9), 32, 32),
+    (K3, 3, 1, (4, 6, 8), 1, 16),
+    (K3, 3, 1, (4, 6, 8), 3, 16),
+    (K3, 3, 1, (4, 4, 8), 64, 48),
+    (K3, 2, 2, (1, 12, 20), 16, 32),
+    (K3, 2, 1, (1, 16, 16), 1, 16),
+    (K1, 3, 2, (4, 6, 8), 32, 16),
+    (K1, 3, 1, (4, 6, 8), 16, 2),
+    (K1, 3, 1, (4, 6, 8), 16, 5),
+    (K1, 3, 1, (4, 6, 8), 1, 16),
+    (K1, 2, 2, (1, 8, 8), 16, 1),
+    (DOWN, 3, 2, (4, 8, 12), 16, 32),
+    (DOWN, 3, 1, (2, 2, 2), 128, 256),
+    (DOWN, 2, 1, (1, 8, 12), 16, 32),
+    (UP, 3, 2, (2, 4, 6), 32, 16),
+    (UP, 3, 1, (1, 1, 1), 256, 128),
+    (UP, 2, 2, (1, 4, 6), 32, 16),
+]
+
+
+def out_spatial(kind, dims, sp):
+    if kind == DOWN:
+        return (sp[0] // 2 if dims == 3 else 1, sp[1] // 2, sp[2] // 2)
+    if kind == UP:
+        return (sp[0] * 2 if dims == 3 else 1, sp[1] * 2, sp[2] * 2)
+    return sp
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind,dims,n,sp,cin,cout", CONV_CASES)
+def test_conv_forward(be, dtype, kind, dims, n, sp, cin, cout):
+    g = torch.Generator().manual_seed(1)
+    k = {K3: 3, K1: 1, DOWN: 2, UP: 2}[kind]
+    kk = (k,) * dims
+    wshape = ((cin, cout) if kind == UP else (cout, cin)) + kk
+    w = torch.randn(wshape, generator=g) * (2.0 / (cin * k ** dims)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    # network-input style x: fp32 even in bf16 mode when cin is not a channel multiple
+    xdt = torch.float32 if cin < 16 else dtype
+    x = sliced(n, sp, cin, xdt, g, pad=16 if cin >= 16 else 0)
+    osp = out_spatial(kind, dims, sp)
+    ydt = torch.float32 if cout < 16 else dtype
+    for with_stats, with_addend in ((True, False), (False, True)):
+        wp_e = EMU.pack_weight(w, kind, "fwd", dtype, dims)
+        wp_c = be.pack_weight(w.cuda(), kind, "fwd", dtype, dims, allow_tc=False)
+        assert torch.equal(wp_c.t.cpu().float(), wp_e.float())
+        y_e = torch.zeros((n,) + osp + (cout,), dtype=ydt)
+        ybuf = torch.zeros((n,) + osp + (cout + 16,), dtype=ydt, device="cuda")
+        y_c = ybuf[..., 8:8 + cout]
+        st_e = torch.zeros(n, cout, 2, dtype=torch.float64) if with_stats else None
+        st_c = dev(st_e.clone()) if with_stats else None
+        add = rnd((n,) + osp + (cout,), ydt, g) if with_addend else None
+        EMU.conv(kind, dims, x, wp_e, bias, y_e, st_e, add)
+        be.conv(kind, dims, x.cuda(), wp_c, bias.cuda(), y_c, st_c, dev(add))
+        torch.cuda.synchronize()
+        assert rel(y_c, y_e) < tol(dtype)
+        assert float(ybuf[..., :8].abs().max()) == 0 and float(ybuf[..., 8 + cout:].abs().max()) == 0
+        if with_stats:
+            assert rel(st_c, st_e) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind,dims,n,sp,cin,cout", CONV_CASES)
+def test_conv_dgrad_and_wgrad(be, dtype, kind, dims, n, sp, cin, cout):
+    """dgrad through b200seg_conv with dgrad-packed weights; wgrad through b200seg_wgrad+unpack;
+    both against autograd of the emulated forward."""
+    g = torch.Generator().manual_seed(2)
+    k = {K3: 3, K1: 1, DOWN: 2, UP: 2}[kind]
+    kk = (k,) * dims
+    wshape = ((cin, cout) if kind == UP else (cout, cin)) + kk
+    w = (torch.randn(wshape, generator=g) * (2.0 / (cin * k ** dims)) ** 0.5)
+    osp = out_spatial(kind, dims, sp)
+    xdt = torch.float32 if cin < 16 else dtype
+    gdt = torch.float32 if cout < 16 else dtype
+    x = rnd((n,) + sp + (cin,), xdt, g)
+    dy = rnd((n,) + osp + (cout,), gdt, g)
+    # reference via autograd in fp64 on the (rounded) operands
+    import torch.nn.functional as F
+    xr = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wq = w.to(dtype).double() if kind != UP else w.to(dtype).double()
+    wr = wq.clone().requires_grad_(True)
+    w5 = wr if dims == 3 else wr.unsqueeze(2)
+    if kind == K3:
+        o = F.conv3d(xr, w5, None, padding=(1 if dims == 3 else 0, 1, 1))
+    elif kind == K1:
+        o = F.conv3d(xr, w5, None)
+    elif kind == DOWN:
+        o = F.conv3d(xr, w5, None, stride=(2 if dims == 3 else 1, 2, 2))
+    else:
+        o = F.conv_transpose3d(xr, w5, None, stride=(2 if dims == 3 else 1, 2, 2))
+    o.backward(dy.double().permute(0, 4, 1, 2, 3))
+    dx_ref = xr.grad.permute(0, 2, 3, 4, 1)
+    # --- dgrad
+    DK = {K3: K3, K1: K1, DOWN: UP, UP: DOWN}[kind]
+    wd = be.pack_weight(w.cuda(), kind, "dgrad", dtype, dims, allow_tc=False)
+    assert torch.equal(wd.t.cpu().float(), EMU.pack_weight(w, kind, "dgrad", dtype, dims).float())
+    if cin >= 16:
+        dx = torch.zeros((n,) + sp + (cin,), dtype=dtype, device="cuda")
+        be.conv(DK, dims, dy.cuda(), wd, None, dx, None, None)
+        torch.cuda.synchronize()
+        assert rel(dx, dx_ref) < tol(dtype)
+    # --- wgrad
+    taps = k ** dims
+    if kind == UP:
+        dwp = torch.zeros((taps, cout, cin), dtype=torch.float32, device="cuda")
+        be.wgrad(DOWN, dims, dy.cuda(), x.cuda(), dwp)
+    else:
+        dwp = torch.zeros((taps, cin, cout), dtype=torch.float32, device="cuda")
+        be.wgrad(kind, dims, x.cuda(), dy.cuda(), dwp)
+    gw = torch.zeros(wshape, dtype=torch.float32, device="cuda")
+    be.unpack_wgrad(dwp, gw, kind, dims)
+    torch.cuda.synchronize()
+    assert rel(gw, wr.grad) < 3e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,sp,c,masked", [(2, (4, 6, 8), 16, True), (1, (3, 5, 7), 32, False),
+                                           (2, (1, 8, 8), 64, True), (1, (2, 2, 2), 256, True)])
+def test_groupnorm_chain(be, dtype, n, sp, c, masked):
+    g = torch.Generator().manual_seed(3)
+    y = sliced(n, sp, c, dtype, g, pad=16)
+    y2 = rnd((n,) + sp + (c,), dtype, g)
+    res = rnd((n,) + sp + (c,), dtype, g)
+    gamma = 1 + 0.2 * torch.randn(c, generator=g)
+    beta = 0.2 * torch.randn(c, generator=g)
+    scale = (torch.rand(n, c, generator=g) > 0.2).float() / 0.8 if masked else None
+    vox = sp[0] * sp[1] * sp[2]
+    yf = y.double()
+    stats = torch.stack([yf.sum((1, 2, 3)), (yf * yf).sum((1, 2, 3))], -1)
+    coef_e, mr_e = torch.empty(n, c, 2), torch.empty(n, 8, 2)
+    EMU.gn_finalize(stats, gamma, beta, scale, vox, 8, 1e-5, coef_e, mr_e)
+    coef_c, mr_c = torch.empty(n, c, 2, device="cuda"), torch.empty(n, 8, 2, device="cuda")
+    be.gn_finalize(stats.cuda(), gamma.cuda(), beta.cuda(), dev(scale), vox, 8, 1e-5, coef_c, mr_c)
+    assert rel(coef_c, coef_e) < 1e-5 and rel(mr_c, mr_e) < 1e-5
+    # apply (all three source forms)
+    for use2, useres in ((False, False), (True, False), (False, True)):
+        out_e = torch.empty((n,) + sp + (c,), dtype=dtype)
+        EMU.apply(y, coef_e, y2 if use2 else None, coef_e if use2 else None, res if useres else None, out_e)
+        obuf = torch.zeros((n,) + sp + (2 * c,), dtype=dtype, device="cuda")
+        out_c = obuf[..., c:]
+        be.apply(y.cuda(), coef_c, dev(y2) if use2 else None, coef_c if use2 else None, dev(res) if useres else None,
+                 out_c)
+        assert rel(out_c, out_e) < tol(dtype, 0.5)
+        assert float(obuf[..., :c].abs().max()) == 0
+    # backward chain
+    gact = rnd((n,) + sp + (c,), dtype, g)
+    sums_e = torch.zeros(n, c, 3, dtype=torch.float64)
+    EMU.gn_bwd_reduce(gact, y, coef_e, sums_e)
+    sums_c = torch.zeros(n, c, 3, dtype=torch.float64, device="cuda")
+    be.gn_bwd_reduce(gact.cuda(), y.cuda(), coef_e.cuda(), sums_c)
+    assert rel(sums_c, sums_e) < 1e-5
+    c3_e = torch.empty(n, c, 3)
+    dg_e, db_e, dbi_e = torch.ones(c), torch.ones(c), torch.zeros(c)
+    EMU.gn_bwd_finalize(sums_e, mr_e, gamma, scale, vox, 8, c3_e, dg_e, db_e, dbi_e)
+    c3_c = torch.empty(n, c, 3, device="cuda")
+    dg_c, db_c, dbi_c = torch.ones(c, device="cuda"), torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    be.gn_bwd_finalize(sums_e.cuda(), mr_e.cuda(), gamma.cuda(), dev(scale), vox, 8, c3_c, dg_c, db_c, dbi_c)
+    for a, b in ((c3_c, c3_e), (dg_c, dg_e), (db_c, db_e)):
+        assert rel(a, b) < 1e-5
+    assert (dbi_c.cpu() - dbi_e).abs().max() < 1e-4 * (1 + dbi_e.abs().max())
+    dy_e = torch.empty((n,) + sp + (c,), dtype=dtype)
+    EMU.gn_bwd_apply(gact, y, coef_e, c3_e, dy_e)
+    dy_c = torch.empty((n,) + sp + (c,), dtype=dtype, device="cuda")
+    be.gn_bwd_apply(gact.cuda(), y.cuda(), coef_e.cuda(), c3_e.cuda(), dy_c)
+    assert rel(dy_c, dy_e) < tol(dtype, 0.5)
+    cs_c = torch.zeros(c, device="cuda")
+    be.colsum(gact.cuda(), cs_c)
+    assert rel(cs_c, gact.double().sum((0, 1, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dims,n,sp,c", [(3, 2, (4, 6, 8), 16), (2, 2, (1, 8, 12), 32), (3, 1, (2, 2, 2), 128)])
+def test_pool(be, dtype, dims, n, sp, c):
+    g = torch.Generator().manual_seed(4)
+    x = torch.relu(sliced(n, sp, c, dtype, g, pad=16))          # ties at zero, like real activations
+    osp = (sp[0] // 2 if dims == 3 else 1, sp[1] // 2, sp[2] // 2)
+    out_e = torch.empty((n,) + osp + (c,), dtype=dtype)
+    EMU.pool_fwd(x, out_e, dims)
+    out_c = torch.empty((n,) + osp + (c,), dtype=dtype, device="cuda")
+    be.pool_fwd(x.cuda(), out_c, dims)
+    assert torch.equal(out_c.cpu().float(), out_e.float())
+    go = rnd((n,) + osp + (c,), dtype, g)
+    add = rnd((n,) + sp + (c,), dtype, g)
+    gx_e = torch.empty((n,) + sp + (c,), dtype=dtype)
+    EMU.pool_bwd(x, go, add, gx_e, dims)
+    gx_c = torch.empty((n,) + sp + (c,), dtype=dtype, device="cuda")
+    be.pool_bwd(x.cuda(), go.cuda(), add.cuda(), gx_c, dims)
+    # positions whose window max is 0 are killed by the ReLU mask downstream; compare where x > 0
+    m = (x > 0).float()
+    assert rel(gx_c.cpu().float() * m, gx_e.float() * m) < tol(dtype, 0.5)
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4, 5, 11])
+def test_head_and_losses(be, c):
+    g = torch.Generator().manual_seed(5)
+    nvox = (2, 5, 6, 7)
+    z = 2 * torch.randn(nvox + (c,), generator=g)
+    t = (torch.rand(nvox, generator=g) > 0.6).long() if c == 1 else torch.randint(0, c, nvox, generator=g)
+    if c > 2:
+        t[t == 1] = 0                      # one absent class
+    p_e = torch.empty_like(z)
+    EMU.head_probs(z, p_e)
+    p_c = torch.empty_like(z, device="cuda")
+    be.head_probs(z.cuda(), p_c)
+    assert (p_c.cpu() - p_e).abs().max() < 2e-6
+    alpha = torch.linspace(0.5, 1.5, c)
+    for terms in (1, 2, 4, 3, 5, 7):
+        for gamma in (2.0, 3.0):
+            npart = 6 if c == 1 else 3 * c + 3
+            part_e = torch.zeros(npart, dtype=torch.float64)
+            EMU.loss_partials(z, t, gamma, 0.25, part_e)
+            part_c = torch.zeros(npart, dtype=torch.float64, device="cuda")
+            be.loss_partials(z.cuda(), t.cuda(), gamma, 0.25, part_c)
+            assert rel(part_c, part_e) < 2e-6
+            nl = 5 if c == 1 else 2 * c + 3
+            loss_e, lc_e = torch.empty(()), torch.empty(nl)
+            EMU.loss_finalize(part_e, c, terms, alpha, gamma, 0.25, loss_e, lc_e)
+            loss_c, lc_c = torch.empty((), device="cuda"), torch.empty(nl, device="cuda")
+            be.loss_finalize(part_e.cuda(), c, terms, alpha.cuda(), gamma, 0.25, loss_c, lc_c)
+            assert abs(loss_c.item() - loss_e.item()) < 1e-6 * max(1, abs(loss_e.item()))
+            assert rel(lc_c, lc_e) < 1e-6
+            gs = torch.tensor([0.7])
+            dz_e = torch.empty_like(z)
+            EMU.loss_bwd(z, t, lc_e, gs, dz_e)
+            dz_c = torch.empty_like(z, device="cuda")
+            be.loss_bwd(z.cuda(), t.cuda(), lc_e.cuda(), gs.cuda(), dz_c)
+            assert (dz_c.cpu() - dz_e).abs().max() < 1e-6 * (1 + dz_e.abs().max()) + 3e-5 * dz_e.abs().max()

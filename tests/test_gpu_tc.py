@@ -1,0 +1,99 @@
+"""tcgen05 + TMA convolution path (bf16) against the test-only PyTorch statement of the op:
+forward and data-gradient forms, 3x3x3 / 3x3 / 1x1, ragged volumes (box overhang), channel-pitched
+(concat-slice) inputs and outputs, fused GroupNorm statistics, fused residual addend.  `-m gpu`."""
+import pytest
+import torch
+
+from emu_backend import EmuBackend, K3, K1
+
+pytestmark = pytest.mark.gpu
+EMU = EmuBackend()
+
+
+@pytest.fixture(scope="module")
+def be():
+    from pytorchdeeplearing_b200._abi import CudaBackend
+    b = CudaBackend()
+    assert b.use_tc
+    return b
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+TC_CASES = [
+    # kind, dims, n, spatial, cin, cout
+    (K3, 3, 1, (8, 8, 16), 16, 16),
+    (K3, 3, 2, (8, 16, 16), 32, 32),
+    (K3, 3, 1, (4, 8, 8), 64, 64),
+    (K3, 3, 1, (4, 4, 8), 128, 128),
+    (K3, 3, 1, (2, 2, 2), 256, 256),      # heavy overhang, 4 k-blocks per tap
+    (K3, 3, 2, (6, 6, 6), 64, 32),        # ragged: no box divides the volume
+    (K3, 3, 1, (12, 12, 12), 16, 48),
+    (K3, 2, 2, (1, 32, 32), 16, 16),
+    (K3, 2, 1, (1, 24, 40), 32, 64),
+    (K1, 3, 2, (8, 8, 8), 32, 16),
+    (K1, 3, 1, (4, 12, 12), 256, 128),
+    (K1, 2, 2, (1, 16, 16), 64, 32),
+]
+
+
+@pytest.mark.parametrize("kind,dims,n,sp,cin,cout", TC_CASES)
+@pytest.mark.parametrize("which", ["fwd", "dgrad"])
+def test_tc_conv_matches_emulation(be, kind, dims, n, sp, cin, cout, which):
+    g = torch.Generator().manual_seed(7)
+    k = 3 if kind == K3 else 1
+    w = torch.randn((cout, cin) + (k,) * dims, generator=g) * (2.0 / (cin * k ** dims)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    dt = torch.bfloat16
+    if which == "fwd":
+        ci, co = cin, cout
+    else:
+        ci, co = cout, cin                 # dgrad: dy (Cout ch) -> dx (Cin ch)
+    xbuf = (torch.randn((n,) + sp + (ci + 16,), generator=g)).to(dt)
+    x = xbuf[..., 8:8 + ci]                # channel-pitched view (concat slice)
+    wp_c = be.pack_weight(w.cuda(), kind, which, dt, dims)
+    assert wp_c.code == 2, "expected the tcgen05 layout"
+    wp_e = EMU.pack_weight(w, kind, which, dt, dims)
+    for with_stats, with_addend, with_bias in ((True, False, True), (False, True, False)):
+        y_e = torch.zeros((n,) + sp + (co,), dtype=dt)
+        ybuf = torch.zeros((n,) + sp + (co + 32,), dtype=dt, device="cuda")
+        y_c = ybuf[..., 16:16 + co]
+        st_e = torch.zeros(n, co, 2, dtype=torch.float64) if with_stats else None
+        st_c = st_e.clone().cuda() if with_stats else None
+        add = torch.randn((n,) + sp + (co,), generator=g).to(dt) if with_addend else None
+        b_ = bias if with_bias else None
+        EMU.conv(kind, dims, x, wp_e, b_, y_e, st_e, add)
+        be.conv(kind, dims, x.cuda(), wp_c, b_.cuda() if with_bias else None, y_c, st_c,
+                add.cuda() if with_addend else None)
+        torch.cuda.synchronize()
+        assert rel(y_c, y_e) < 6e-3, rel(y_c, y_e)
+        assert float(ybuf[..., :16].abs().max()) == 0 and float(ybuf[..., 16 + co:].abs().max()) == 0
+        if with_stats:
+            assert rel(st_c, st_e) < 1e-4, rel(st_c, st_e)
+
+
+def test_tc_conv_large_volume_many_tiles(be):
+    """more tiles than SMs -> persistent loop, both accumulator stages, stage ring wrap-around"""
+    g = torch.Generator().manual_seed(8)
+    n, sp, c = 2, (48, 48, 48), 32
+    dt = torch.bfloat16
+    w = torch.randn((c, c, 3, 3, 3), generator=g) * (2.0 / (c * 27)) ** 0.5
+    x = torch.randn((n,) + sp + (c,), generator=g).to(dt)
+    wp_c = be.pack_weight(w.cuda(), K3, "fwd", dt, 3)
+    wp_e = EMU.pack_weight(w, K3, "fwd", dt, 3)
+    y_e = torch.zeros((n,) + sp + (c,), dtype=dt)
+    st_e = torch.zeros(n, c, 2, dtype=torch.float64)
+    EMU.conv(K3, 3, x, wp_e, None, y_e, st_e, None)
+    y_c = torch.zeros((n,) + sp + (c,), dtype=dt, device="cuda")
+    st_c = torch.zeros(n, c, 2, dtype=torch.float64, device="cuda")
+    be.conv(K3, 3, x.cuda(), wp_c, None, y_c, st_c, None)
+    torch.cuda.synchronize()
+    assert rel(y_c, y_e) < 6e-3
+    assert rel(st_c, st_e) < 1e-4
+    # determinism of the statistics path (fixed-order reductions; fp64 atomics differ at 1e-16)
+    y2 = torch.zeros_like(y_c)
+    be.conv(K3, 3, x.cuda(), wp_c, None, y2, None, None)
+    assert torch.equal(y2, y_c)
