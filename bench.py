@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""Headline benchmark: VNet3d(1,2) 96^3, batch 2 per GPU, bf16 storage, forward + loss + backward
+(+ gradient all-reduce for N > 1) in voxels/second (BASELINE.json `metric`, config[1] / config[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-graph]
+
+N > 1 is launched by the driver as ``python -m torch.distributed.run --nproc-per-node N bench.py --gpus N``
+(one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.  A "step" = one pass of the hot path
+(forward in train mode with dropout masks drawn, MutilDiceLoss, backward of all 128 parameter
+tensors; no optimizer -- the metric is "fwd+bwd") over one synthetic batch.
+
+Timing: CUDA events on the launching stream, one event pair per step, L2 flushed (256 MiB write)
+before every timed step outside the event pair, max over ranks; W >= 3 warm-up steps.
+  value : inputs resident in HBM, CUDA-graph replay of the step captured through the public API.
+  e2e   : same, but every step copies x (fp32) and labels (int64) from pinned host memory and reads
+          the loss back to the host inside the timed region.
+  roofline     : the dominant kernel of the step (per-kernel CUDA-event timing of one eager step),
+                 algorithmic bytes/flops / its mean duration vs MEASURED_PEAKS.json.
+  cpu_baseline : the CPU oracle (oracle/, a restatement of the reference's PyTorch path: "port")
+                 timed on this box's host cores, same shapes/seeds, fwd+loss+bwd, rank 0, N=1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SPATIAL = (96, 96, 96)
+BATCH_PER_GPU = 2
+NUMCLASS = 2
+# algorithmic work of one fwd+bwd step of VNet3d(1,2) 96^3 B=2 (bf16 storage)
+STEP_GFLOP = 433.11
+STEP_MB = 3239.9
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "bf16_tflops_burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel timing wrapper (instrumentation around the real CudaBackend)
+# ------------------------------------------------------------------------------------------------
+class TimedBackend:
+    TIMED = ("conv", "wgrad", "apply", "gn_bwd_reduce", "gn_bwd_apply", "gn_finalize", "gn_bwd_finalize",
+             "pack_weight", "unpack_wgrad", "colsum", "head_probs", "loss_partials", "loss_finalize", "loss_bwd",
+             "pool_fwd", "pool_bwd")
+
+    def __init__(self, inner):
+        self.inner, self.records = inner, []
+
+    def __getattr__(self, name):
+        fn = getattr(self.inner, name)
+        if name not in self.TIMED:
+            return fn
+
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.records.append((name, self._describe(name, a), e0, e1, self._work(name, a)))
+            return r
+        return wrapped
+
+    @staticmethod
+    def _describe(name, a):
+        if name == "conv":
+            kind, dims, x, wpk, bias, y = a[:6]
+            tc = getattr(wpk, "code", 0) == 2
+            return f"conv[k{kind}{'/tcgen05' if tc else '/ffma'}] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
+        if name == "wgrad":
+            kind, dims, x, dy = a[:4]
+            return f"wgrad[k{kind}] {x.shape[-1]}x{dy.shape[-1]}@{tuple(dy.shape[1:4])}"
+        t = next((v for v in a if isinstance(v, torch.Tensor) and v.dim() == 5), None)
+        return f"{name} {t.shape[-1]}@{tuple(t.shape[1:4])}" if t is not None else name
+
+    @staticmethod
+    def _work(name, a):
+        """(algorithmic bytes, algorithmic flops) of one launch."""
+        def nbytes(t):
+            return 0 if t is None else t.numel() * t.element_size()
+        if name == "conv":
+            kind, dims, x, wpk, bias, y, stats, addend = a[:8]
+            w = wpk.t if hasattr(wpk, "t") else wpk
+            taps_cin = w.numel() // y.shape[-1]
+            vox_out = y.numel() // y.shape[-1]
+            if kind == 3:  # UP: K = Cin per fine voxel
+                flops = 2.0 * vox_out * y.shape[-1] * x.shape[-1]
+            else:
+                flops = 2.0 * vox_out * y.shape[-1] * taps_cin
+            return nbytes(x) + nbytes(y) + nbytes(w) + nbytes(addend), flops
+        if name == "wgrad":
+            kind, dims, x, dy, dwp = a[:5]
+            vox = dy.numel() // dy.shape[-1]
+            return nbytes(x) + nbytes(dy) + nbytes(dwp), 2.0 * vox * dwp.numel()
+        b = sum(nbytes(v) for v in a if isinstance(v, torch.Tensor) and v.dim() == 5)
+        return b, 0.0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, desc, e0, e1, (by, fl) in self.records:
+            ms = e0.elapsed_time(e1)
+            d = agg.setdefault(desc, {"ms": 0.0, "n": 0, "bytes": by, "flops": fl})
+            d["ms"] += ms
+            d["n"] += 1
+        return agg
+
+
+# ------------------------------------------------------------------------------------------------
+def make_batch(rank: int, world: int):
+    """global batch = 2*world samples drawn from one seeded generator; rank r takes [2r, 2r+2)."""
+    import oracle
+    x, y = oracle.make_inputs(BATCH_PER_GPU * world, 1, SPATIAL, NUMCLASS, seed=1234)
+    sl = slice(BATCH_PER_GPU * rank, BATCH_PER_GPU * (rank + 1))
+    return x[sl].contiguous(), y[sl].contiguous()
+
+
+def run_reference(args):
+    """The reference's own CPU path for this metric: the oracle restatement (kind 'port') on all host cores."""
+    import oracle
+    from oracle import nets as onets
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = pick_cpu_threads()
+    torch.set_num_threads(cores)
+    spec = onets.vnet3d_state_spec(1, NUMCLASS)
+    sd = {k: v.requires_grad_(True) for k, v in onets.init_state_dict(spec, seed=0).items()}
+    x, y = make_batch(0, 1)
+    alpha = torch.ones(NUMCLASS)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        masks = onets.draw_dropout_masks_vnet3d(x.shape[0])
+        logits, _ = onets.vnet3d_forward(sd, x, masks)
+        loss = oracle.loss_forward("MutilDiceLoss", logits, y, alpha)
+        loss.backward()
+        return float(loss)
+
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    vox = BATCH_PER_GPU * SPATIAL[0] * SPATIAL[1] * SPATIAL[2]
+    val = vox / t
+    line = {"impl": "reference", "metric": "voxels_per_sec_fwd_bwd", "value": val, "unit": "voxels/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "VNet3d(1,2) 96x96x96 batch 2, fwd+loss(MutilDice)+bwd, train mode, CPU fp32",
+                       "global_batch": BATCH_PER_GPU},
+            "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{steps} full steps (2x96^3 voxels each) of the oracle restatement on "
+                                       f"{torch.get_num_threads()} host threads"},
+            "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def pick_cpu_threads():
+    """Host threads for the CPU arm: all cores the process may use, unless a short probe (one 3x3x3
+    conv at the 32-channel level) shows fewer threads are faster on this (shared) host."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    xs = torch.randn(2, 32, 48, 48, 48)
+    ws = torch.randn(32, 32, 3, 3, 3)
+    best, best_t = avail, None
+    cand = sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 32), min(avail, 16)}, reverse=True)
+    for th in cand:
+        torch.set_num_threads(th)
+        torch.nn.functional.conv3d(xs, ws, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv3d(xs, ws, padding=1)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = th, dt
+    return best
+
+
+def cpu_baseline_sample():
+    import oracle
+    from oracle import nets as onets
+    prev = torch.get_num_threads()
+    cores = pick_cpu_threads()
+    torch.set_num_threads(cores)
+    spec = onets.vnet3d_state_spec(1, NUMCLASS)
+    sd = {k: v.requires_grad_(True) for k, v in onets.init_state_dict(spec, seed=0).items()}
+    x, y = make_batch(0, 1)
+    alpha = torch.ones(NUMCLASS)
+    ts = []
+    for i in range(3):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        masks = onets.draw_dropout_masks_vnet3d(x.shape[0])
+        logits, _ = onets.vnet3d_forward(sd, x, masks)
+        loss = oracle.loss_forward("MutilDiceLoss", logits, y, alpha)
+        loss.backward()
+        if i > 0:
+            ts.append(time.perf_counter() - t0)
+    torch.set_num_threads(prev)
+    t = statistics.median(ts)
+    vox = BATCH_PER_GPU * SPATIAL[0] * SPATIAL[1] * SPATIAL[2]
+    return {"value": vox / t, "unit": "voxels/s", "cores": cores, "kind": "port",
+            "sample": f"2 timed full steps (+1 warm-up) of VNet3d 96^3 B=2 fwd+loss+bwd, oracle restatement, fp32, "
+                      f"{cores} host threads; median {t * 1e3:.0f} ms/step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import pytorchdeeplearing_b200 as b200
+    from pytorchdeeplearing_b200 import runtime
+    from pytorchdeeplearing_b200.graphed import GraphedStep
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the b200 arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        b200.enable_data_parallel()
+    b200.set_precision(args.precision)
+
+    torch.manual_seed(0)
+    model = b200.VNet3d(1, NUMCLASS)
+    model.apply(b200.initialize_weights)
+    model = model.to(dev).train()
+    lossfn = b200.MutilDiceLoss(torch.ones(NUMCLASS, device=dev))
+    xh, yh = make_batch(rank, world)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    x, y = xh.to(dev), yh.to(dev)
+    torch.manual_seed(100 + rank)
+    be = runtime.cuda_backend()
+
+    def eager_step(xx, yy):
+        for p in model.parameters():
+            p.grad = None
+        logits, _ = model(xx)
+        loss = lossfn(logits, yy)
+        loss.backward()
+        return loss
+
+    # ---- launches per step + per-kernel timing (one eager, instrumented step)
+    eager_step(x, y)
+    torch.cuda.synchronize()
+    c0 = be.launch_count
+    tb = TimedBackend(be)
+    runtime._set_backend_for_testing(tb)
+    eager_step(x, y)
+    runtime._set_backend_for_testing(None)
+    launches = be.launch_count - c0
+    kern = tb.summary()
+
+    use_graph = not args.no_graph
+    graphed = None
+    if use_graph:
+        try:
+            graphed = GraphedStep(model, lossfn, x, y, warmup=1)
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches",
+                      file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, k):
+        evs = []
+        for _ in range(k):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def resident_step():
+        if use_graph:
+            graphed.graph.replay()
+        else:
+            eager_step(x, y)
+
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        if use_graph:
+            loss = graphed(xh, yh)
+        else:
+            loss = eager_step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
+        host_loss.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    ms = timed(resident_step, args.steps)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ms_e2e = timed(e2e_step, args.steps)
+    barrier()
+
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    t_step = tot[0].item() / args.steps * 1e-3
+    t_e2e = tot[1].item() / args.steps * 1e-3
+    vox_step = world * BATCH_PER_GPU * SPATIAL[0] * SPATIAL[1] * SPATIAL[2]
+
+    if rank == 0:
+        peaks = load_peaks()
+        # dominant kernel of the step
+        top = max(kern.items(), key=lambda kv: kv[1]["ms"])
+        desc, d = top
+        dur = d["ms"] / d["n"] * 1e-3
+        gbs = d["bytes"] / dur / 1e9
+        tfs = d["flops"] / dur / 1e12
+        hbm_frac = gbs / peaks["hbm_gbs"]
+        tc_frac = tfs / peaks["bf16_tflops_burst"]
+        if tc_frac > hbm_frac:
+            roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["bf16_tflops_burst"], "unit": "TFLOP/s",
+                    "frac": tc_frac}
+        else:
+            roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
+        roof.update({"kernel": desc, "launches_per_step": d["n"], "avg_us": dur * 1e6, "traffic": None,
+                     "peaks": peaks["source"],
+                     "share_of_step": d["ms"] / max(1e-9, sum(v["ms"] for v in kern.values()))})
+        ranked = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:12]
+        step_roof = {"hbm_GBps": STEP_MB / 1e3 / t_step, "tflops": STEP_GFLOP / 1e3 / t_step,
+                     "frac_hbm": STEP_MB / 1e3 / t_step / peaks["hbm_gbs"],
+                     "frac_tensor": STEP_GFLOP / 1e3 / t_step / peaks["bf16_tflops"],
+                     "algorithmic_GFLOP": STEP_GFLOP, "algorithmic_MB": STEP_MB}
+        line = {
+            "metric": "voxels_per_sec_fwd_bwd", "value": vox_step / t_step, "unit": "voxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "VNet3d(1,2) 96x96x96, batch 2 per GPU, fwd (train mode, dropout masks drawn) + "
+                                   "MutilDiceLoss + bwd of all 128 parameter tensors"
+                                   + (" + NCCL SUM all-reduce of the flat fp32 gradient bucket" if world > 1 else ""),
+                       "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
+                       "l2": "256 MiB flush before every timed step; per-step working set > 1 GB >> 126 MB L2",
+                       "cuda_graph": use_graph, "precision_mode": args.precision},
+            "e2e": {"value": vox_step / t_e2e, "unit": "voxels/s", "ms_per_step": t_e2e * 1e3,
+                    "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "clocks": clocks, "roofline": roof, "roofline_step": step_roof,
+            "top_kernels": [{"kernel": k, "ms_per_step": v["ms"], "launches": v["n"]} for k, v in ranked],
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

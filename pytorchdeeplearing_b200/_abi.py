@@ -135,6 +135,7 @@ class CudaBackend:
         self._inited = set()
         # B200SEG_DISABLE_TC=1 forces every conv onto the CUDA-core implicit-GEMM kernels (debug / A-B timing)
         self.use_tc = os.environ.get("B200SEG_DISABLE_TC", "0") != "1"
+        self.launch_count = 0      # kernels launched through the C ABI (one per successful entry-point call)
 
     # ------------------------------------------------------------------ plumbing
     def _ds(self, t: torch.Tensor):
@@ -148,6 +149,7 @@ class CudaBackend:
         if rc != 0:
             msg = self.lib.b200seg_last_error()
             raise RuntimeError(f"libb200seg error {rc}: {msg.decode() if msg else ''}")
+        self.launch_count += 1
 
     # ------------------------------------------------------------------ weights
     def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True):

@@ -1,5 +1,6 @@
 // extern "C" surface of libb200seg.so (see include/b200seg.h for the contract).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,6 +25,9 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
             double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
 int conv_tc_init(int device);
 int conv_tc_channels_ok(int kind, int cin, int cout);
+int wgrad_tc_supported(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b);
+int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+             cudaStream_t st);
 int wgrad_generic(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
                   cudaStream_t st);
 int ew_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N2, int N1, long long st,
@@ -118,6 +122,15 @@ int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_ten
   B200_CHECK_ARG(dwp != nullptr, "b200seg_wgrad: null output");
   B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_wgrad: dims must be 2 or 3");
   B200_DEVICE(device);
+  static const bool tc_off = [] {
+    const char* e = getenv("B200SEG_DISABLE_TC_WGRAD");
+    const char* e2 = getenv("B200SEG_DISABLE_TC");
+    return (e && e[0] == '1') || (e2 && e2[0] == '1');
+  }();
+  if (!tc_off && wgrad_tc_supported(kind, dims, a, b)) {
+    if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
+    return wgrad_tc(kind, dims, a, b, dwp, device, ST(stream));
+  }
   return wgrad_generic(kind, dims, a, b, dwp, device, ST(stream));
 }
 

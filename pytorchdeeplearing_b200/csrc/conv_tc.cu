@@ -15,138 +15,27 @@
 // epilogue (tcgen05.ld -> +bias -> GroupNorm sum/sumsq partials -> +addend -> bf16 NDHWC stores).
 // Two accumulator stages in TMEM overlap the epilogue of tile i with the main loop of tile i+1;
 // CTAs are persistent over contiguous tile ranges (grid = min(tiles, #SM)).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b200seg {
 
 // ------------------------------------------------------------------------------------------------
-// driver entry point (no -lcuda: resolved lazily so the library loads on machines without a driver)
+// driver entry point
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-static int resolve_driver() {
-  if (g_encode) return 0;
+EncodeTiledFn tc_encode_fn() {
+  if (g_encode) return g_encode;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
     (void)cudaGetLastError();
     set_error("cannot resolve cuTensorMapEncodeTiled from the CUDA driver");
-    return -1;
+    return nullptr;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-      "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets TMEM lane (base_lane + i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, swizzled operand tile (rows of `swizzle_bytes`, 8-row atoms): SBO = 8 * swizzle_bytes
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t swizzle_bytes) {
-  const uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
-  const uint64_t sbo = (uint64_t)(8u * swizzle_bytes) >> 4;
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
+  return g_encode;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -414,7 +303,7 @@ int conv_tc_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, 
   return 1;
 }
 
-static void pick_box(int W, int H, int D, int* bw, int* bh, int* bd) {
+void tc_pick_box(int W, int H, int D, int* bw, int* bh, int* bd) {
   long long best = -1;
   int bb[3] = {16, 8, 1};
   for (int w = 1; w <= 128; w *= 2)
@@ -434,6 +323,9 @@ static void pick_box(int W, int H, int D, int* bw, int* bh, int* bd) {
 
 static int g_smem_optin[64] = {0};
 
+int wgrad_tc_init(int device, int maxsm);
+int tc_max_smem(int device) { return (device >= 0 && device < 64 && g_smem_optin[device] > 0) ? g_smem_optin[device] : 227 * 1024; }
+
 int conv_tc_init(int device) {
   if (device < 0 || device >= 64) return B200SEG_OK;
   if (g_smem_optin[device]) return B200SEG_OK;
@@ -442,13 +334,14 @@ int conv_tc_init(int device) {
   B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
   B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
   B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+  if (wgrad_tc_init(device, maxsm) != B200SEG_OK) return B200SEG_ECUDA;
   g_smem_optin[device] = maxsm;
   return B200SEG_OK;
 }
 
 int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
             double* stats, const b200seg_tensor* addend, int device, cudaStream_t st) {
-  if (resolve_driver() != 0) return B200SEG_ECUDA;
+  if (tc_encode_fn() == nullptr) return B200SEG_ECUDA;
   if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
   ConvGeom g;
   conv_geometry(kind, dims, &g);
@@ -462,7 +355,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   p.N = x->n; p.D = x->d; p.H = x->h; p.W = x->w;
   p.Cin = x->c; p.Cout = y->c;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
-  pick_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd);
+  tc_pick_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd);
   p.tw = (p.W + p.bw - 1) / p.bw;
   p.th = (p.H + p.bh - 1) / p.bh;
   p.td = (p.D + p.bd - 1) / p.bd;

@@ -37,8 +37,20 @@ def act_dtype() -> torch.dtype:
 
 
 def _set_backend_for_testing(backend) -> None:
+    """Instrumentation / test hook: route every op through ``backend`` (an object with the
+    ``CudaBackend`` method set).  Used by the CPU test-suite (emulated ops) and by bench.py's per-kernel
+    timing wrapper around the real ``CudaBackend``; ``None`` restores the product backend."""
     global _TEST_BACKEND
     _TEST_BACKEND = backend
+
+
+def cuda_backend():
+    """The process-wide ``CudaBackend`` (created on first use; raises without a CUDA device)."""
+    global _CUDA_BACKEND
+    if _CUDA_BACKEND is None:
+        from . import _abi
+        _CUDA_BACKEND = _abi.CudaBackend()
+    return _CUDA_BACKEND
 
 
 def get_backend(t: torch.Tensor):
@@ -48,11 +60,7 @@ def get_backend(t: torch.Tensor):
         raise RuntimeError(
             "pytorchdeeplearing_b200 runs only on a CUDA (sm_100a) device: got a tensor on "
             f"'{t.device}'. There is no CPU fallback -- move the model and inputs to cuda.")
-    global _CUDA_BACKEND
-    if _CUDA_BACKEND is None:
-        from . import _abi
-        _CUDA_BACKEND = _abi.CudaBackend()
-    return _CUDA_BACKEND
+    return cuda_backend()
 
 
 # ---------------------------------------------------------------------------- data parallel

@@ -36,6 +36,10 @@ class Recorder:
 
         def wrapped(*a, **k):
             r = fn(*a, **k)
+            if name == "gn_bwd_apply":
+                self.last_bwd_apply_inputs = [t.detach().cpu().clone() for t in a[:4]]
+                self.bwd_apply_inputs = getattr(self, "bwd_apply_inputs", [])
+                self.bwd_apply_inputs.append((len(self.log), self.last_bwd_apply_inputs))
             if name in OUT_ARGS:
                 outs = [a[i] for i in OUT_ARGS[name] if i < len(a) and isinstance(a[i], torch.Tensor)]
                 tag = name
@@ -88,7 +92,39 @@ def main():
             errs.append(((a - b).norm() / (b.norm() + 1e-300)).item())
         worst = max(errs) if errs else 0.0
         flag = " <<<" if worst > (1e-4 if mode == "fp32" else 2e-2) else ""
-        print(f"{i:4d} {tc:18s} {str(sc[0]) if sc else '':28s} " + " ".join(f"{e:.2e}" for e in errs) + flag)
+        extra = ""
+        if tc.startswith("gn_bwd_apply") and oc:
+            d = (oc[0] - oe[0]).abs()
+            big = int((d > 0.05 * oe[0].abs().max()).sum())
+            extra = f"  [outliers>5%max: {big}, err^2 share of top-8: {(d.flatten().topk(8).values ** 2).sum() / (d ** 2).sum():.3f}]"
+        print(f"{i:4d} {tc:18s} {str(sc[0]) if sc else '':28s} " + " ".join(f"{e:.2e}" for e in errs) + flag + extra)
+    # kernel arithmetic in isolation: re-evaluate the first badly diverging gn_bwd_apply on the CUDA run's
+    # own inputs with the emulation formula
+    emu = EmuBackend()
+    shown = 0
+    for (idx, ins_c), (_, ins_e) in zip(rc.bwd_apply_inputs, re_.bwd_apply_inputs):
+        oc, oe = rc.log[idx][1][0], re_.log[idx][1][0]
+        err = ((oc - oe).norm() / oe.norm()).item()
+        if err < 1e-4 or shown >= 2:
+            continue
+        shown += 1
+        g, y, coef, coef3 = ins_c
+        out = torch.empty_like(g)
+        emu.gn_bwd_apply(g, y, coef, coef3, out)
+        print(f"op {idx}: cuda-out vs emu(formula on cuda inputs): {((oc - out.double()).norm() / oc.norm()).item():.3e}")
+        ge, ye, coefe, coef3e = ins_e
+        n = y.shape[0]
+        v = lambda t, i: t[..., i].view(n, 1, 1, 1, -1)
+        pre_c = torch.addcmul(v(coef, 1), y.float(), v(coef, 0))
+        pre_e = torch.addcmul(v(coefe, 1), ye.float(), v(coefe, 0))
+        flips = (pre_c > 0) != (pre_e > 0)
+        print(f"   mask flips between runs: {int(flips.sum())}; |pre| at flips: {pre_c[flips].abs().tolist()[:8]}")
+        print(f"   exact zeros in pre-activation (cuda inputs): {int((pre_c == 0).sum())}; y==0: {int((y == 0).sum())}")
+        d = (oc - oe).abs().flatten()
+        top = d.topk(8)
+        for val, ix in zip(top.values.tolist(), top.indices.tolist()):
+            print(f"   idx {ix}: |diff| {val:.3e} cuda {oc.flatten()[ix]:.4e} emu {oe.flatten()[ix]:.4e} "
+                  f"pre_c {pre_c.flatten()[ix]:.4e} pre_e {pre_e.flatten()[ix]:.4e} g {g.flatten()[ix]:.4e}")
     print("---- parameter gradients (cuda vs emu)")
     for n in gc:
         e = ((gc[n] - ge[n]).norm() / (ge[n].norm() + 1e-300)).item()

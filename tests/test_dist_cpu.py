@@ -1,0 +1,71 @@
+"""Data-parallel host logic on CPU (gloo, world_size 2) with the emulated backend: batch sharding
+with (a) the all-reduce of the loss partial sums (global-batch-exact Dice) and
+(b) the SUM all-reduce of the flat gradient bucket must reproduce the single-process result on the
+global batch."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, arch, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from oracle import nets as onets
+    import pytorchdeeplearing_b200 as b200
+    from pytorchdeeplearing_b200 import runtime
+    from emu_backend import EmuBackend
+    runtime._set_backend_for_testing(EmuBackend())
+    runtime.set_precision("fp32")
+    if arch == "vnet3d":
+        model, ncls, sp, lossfn = b200.VNet3d(1, 2), 2, (16, 16, 16), b200.MutilCrossEntropyDiceLoss(torch.ones(2))
+    else:
+        model, ncls, sp, lossfn = b200.UNet2d(1, 1), 1, (32, 32), b200.BinaryDiceFocalLoss()
+    spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(onets.init_state_dict(spec, seed=4, randomize_affine=True))
+    model.eval()
+    x, y = oracle.make_inputs(2 * world, 1, sp, ncls, seed=9)
+    # single-process result on the GLOBAL batch (no collectives)
+    logits, _ = model(x)
+    loss_g = lossfn(logits, y)
+    loss_g.backward()
+    ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    # sharded: rank r takes samples [2r, 2r+2)
+    b200.enable_data_parallel()
+    sl = slice(2 * rank, 2 * rank + 2)
+    logits, _ = model(x[sl])
+    loss = lossfn(logits, y[sl])
+    loss.backward()
+    b200.disable_data_parallel()
+    err = max(((p.grad - ref[n]).norm() / (ref[n].norm() + 1e-12)).item() for n, p in model.named_parameters())
+    q.put((rank, abs(loss.item() - loss_g.item()), err))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("arch", ["vnet3d", "unet2d"])
+def test_two_rank_sharding_matches_global_batch(arch):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, arch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, dloss, gerr in res:
+        assert dloss < 1e-6, (rank, dloss)          # loss equals the global-batch loss on every rank
+        assert gerr < 1e-4, (rank, gerr)            # summed gradients equal the global-batch gradients

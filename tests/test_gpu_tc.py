@@ -46,14 +46,16 @@ def test_tc_conv_matches_emulation(be, kind, dims, n, sp, cin, cout, which):
     g = torch.Generator().manual_seed(7)
     k = 3 if kind == K3 else 1
     w = torch.randn((cout, cin) + (k,) * dims, generator=g) * (2.0 / (cin * k ** dims)) ** 0.5
-    bias = torch.randn(cout, generator=g) * 0.1
     dt = torch.bfloat16
     if which == "fwd":
         ci, co = cin, cout
     else:
         ci, co = cout, cin                 # dgrad: dy (Cout ch) -> dx (Cin ch)
+    bias = torch.randn(co, generator=g) * 0.1
     xbuf = (torch.randn((n,) + sp + (ci + 16,), generator=g)).to(dt)
     x = xbuf[..., 8:8 + ci]                # channel-pitched view (concat slice)
+    if not be.lib.b200seg_conv_tc_eligible(kind, ci, co):
+        pytest.skip("shape not on the tcgen05 path")
     wp_c = be.pack_weight(w.cuda(), kind, which, dt, dims)
     assert wp_c.code == 2, "expected the tcgen05 layout"
     wp_e = EMU.pack_weight(w, kind, which, dt, dims)
@@ -97,3 +99,39 @@ def test_tc_conv_large_volume_many_tiles(be):
     y2 = torch.zeros_like(y_c)
     be.conv(K3, 3, x.cuda(), wp_c, None, y2, None, None)
     assert torch.equal(y2, y_c)
+
+
+WG_CASES = [
+    # kind, dims, n, spatial, ka (x channels), kb (dy channels)
+    (K3, 3, 1, (8, 8, 16), 16, 16),
+    (K3, 3, 2, (8, 16, 16), 32, 32),
+    (K3, 3, 1, (8, 8, 8), 64, 64),
+    (K3, 3, 1, (4, 4, 8), 128, 128),
+    (K3, 3, 1, (2, 4, 4), 256, 256),
+    (K3, 3, 2, (6, 6, 6), 32, 16),        # ragged volume; UNet decoder shape 2C -> C
+    (K3, 2, 2, (1, 32, 32), 16, 16),
+    (K3, 2, 1, (1, 24, 40), 64, 32),
+    (K1, 3, 2, (8, 8, 8), 32, 16),
+    (K1, 3, 1, (4, 12, 12), 256, 128),
+    (K3, 3, 2, (24, 24, 24), 32, 32),     # more voxel tiles than one CTA chunk
+]
+
+
+@pytest.mark.parametrize("kind,dims,n,sp,ka,kb", WG_CASES)
+def test_tc_wgrad_matches_emulation(be, kind, dims, n, sp, ka, kb):
+    g = torch.Generator().manual_seed(9)
+    dt = torch.bfloat16
+    abuf = torch.randn((n,) + sp + (ka + 16,), generator=g).to(dt)
+    a = abuf[..., 8:8 + ka]                    # pitched view
+    b = torch.randn((n,) + sp + (kb,), generator=g).to(dt)
+    taps = (27 if dims == 3 else 9) if kind == K3 else 1
+    dw_e = torch.zeros(taps, ka, kb)
+    EMU.wgrad(kind, dims, a, b, dw_e)
+    dw_c = torch.zeros(taps, ka, kb, device="cuda")
+    be.wgrad(kind, dims, a.cuda(), b.cuda(), dw_c)
+    torch.cuda.synchronize()
+    assert rel(dw_c, dw_e) < 2e-5, rel(dw_c, dw_e)
+    # accumulation semantics (+=)
+    be.wgrad(kind, dims, a.cuda(), b.cuda(), dw_c)
+    torch.cuda.synchronize()
+    assert rel(dw_c, 2 * dw_e) < 2e-5
