@@ -121,6 +121,18 @@ int b200seg_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dim
 int b200seg_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* g_out, const b200seg_tensor* addend,
                      const b200seg_tensor* g_x, int dims, int device, b200seg_stream stream);
 
+/* ---- fused head (OutputTransition3d, VNet3d.py:90-99; Unet3d.py:56-61): 1x1 conv to `nc` <= 8 classes + bias,
+ * then sigmoid (nc == 1) or softmax over classes.  w: the nn.Conv parameter itself, fp32 [nc][Cin]; logits and
+ * probs: fp32 channels-last [voxels][nc]. */
+int b200seg_head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* logits, float* probs, int nc,
+                     int device, b200seg_stream stream);
+/* backward of the head conv in one pass: dx = dlogits * W (same dtype as x), dw[nc][Cin] += dlogits^T x,
+ * db[nc] += sum dlogits.  Returns B200SEG_EINVAL for shapes outside the fused path (nc > 4, Cin not 16/32):
+ * query with b200seg_head_bwd_supported and use b200seg_conv / b200seg_wgrad / b200seg_colsum instead. */
+int b200seg_head_bwd_supported(int cin, int nc);
+int b200seg_head_bwd(const b200seg_tensor* x, const float* dlogits, const float* w, const b200seg_tensor* dx,
+                     float* dw, float* db, int nc, int device, b200seg_stream stream);
+
 /* ---- head activation: torch.sigmoid / torch.softmax(dim=1) (VNet3d.py:95-98; Unet3d.py:58-61) */
 int b200seg_head_probs(const float* logits, float* probs, int64_t nvox, int C, int device, b200seg_stream stream);
 

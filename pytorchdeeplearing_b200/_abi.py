@@ -46,6 +46,9 @@ _SIGNATURES = {
     "b200seg_pool_fwd": ([_PT, _PT, _i, _i, _vp], C.c_int),
     "b200seg_pool_bwd": ([_PT, _PT, _PT, _PT, _i, _i, _vp], C.c_int),
     "b200seg_head_probs": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
+    "b200seg_head_fwd": ([_PT, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
+    "b200seg_head_bwd_supported": ([_i, _i], C.c_int),
+    "b200seg_head_bwd": ([_PT, _vp, _vp, _PT, _vp, _vp, _i, _i, _vp], C.c_int),
     "b200seg_loss_partials": ([_vp, _vp, _i64, _i, _f, _f, _vp, _i, _vp], C.c_int),
     "b200seg_loss_finalize": ([_vp, _i, _i, _vp, _f, _f, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_loss_bwd": ([_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp], C.c_int),
@@ -159,17 +162,26 @@ class CudaBackend:
         od = F32 if dtype == torch.float32 else BF16
         code = od
         tc = False
-        if allow_tc and self.use_tc and dtype == torch.bfloat16 and kind in (K3, K1):
-            cin, cout = (b, a) if which == "fwd" else (a, b)
-            tc = bool(self.lib.b200seg_conv_tc_eligible(kind, cin, cout))
+        if allow_tc and self.use_tc and dtype == torch.bfloat16:
+            # (kind, Cin, Cout) of the op that will consume the packed operand
+            if which == "fwd":
+                op = (kind, a, b) if kind == UP else (kind, b, a)
+            else:
+                op = {K3: (K3, a, b), K1: (K1, a, b), DOWN: (UP, a, b), UP: (DOWN, b, a)}[kind]
+            tc = bool(self.lib.b200seg_conv_tc_eligible(*op))
         if tc:
+            # K-major rows for the tcgen05 path: [tap][N][K]
             code = BF16_TC
-            if which == "fwd":     # W (Co,Ci,t) -> [t][co][ci]
-                out = torch.empty((t, a, b), dtype=dtype, device=w.device)
-                args = (t, a, 1, b, 1, b * t, 0, t, 0)
-            else:                  # [T-1-t][ci][co]
+            gather_like = (which == "fwd" and kind != UP) or (which == "dgrad" and kind == UP)
+            if which == "dgrad" and kind in (K3, K1):      # [T-1-t][ci][co]
                 out = torch.empty((t, b, a), dtype=dtype, device=w.device)
                 args = (t, b, 1, a, 1, t, 0, b * t, 1)
+            elif gather_like:                               # W (A,B,t) -> [t][A][B]
+                out = torch.empty((t, a, b), dtype=dtype, device=w.device)
+                args = (t, a, 1, b, 1, b * t, 0, t, 0)
+            else:                                           # W (A,B,t) -> [t][B][A]  (UP fwd, DOWN dgrad)
+                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
+                args = (t, b, 1, a, 1, t, 0, b * t, 0)
         elif which == "fwd":
             if kind == UP:      # W (Ci,Co,t) -> [ci][t*Co + co]
                 out = torch.empty((a, t * b), dtype=dtype, device=w.device)
@@ -264,6 +276,27 @@ class CudaBackend:
         dev, st = self._ds(logits)
         c = logits.shape[-1]
         self._check(self.lib.b200seg_head_probs(logits.data_ptr(), probs.data_ptr(), logits.numel() // c, c, dev, st))
+
+    def head_fwd(self, x, w, bias, logits, probs):
+        """logits/probs (N,D,H,W,nc) fp32 contiguous; w the (nc,Cin,1..) conv parameter. False if unsupported."""
+        nc = logits.shape[-1]
+        if nc > 8 or x.shape[-1] % 4 != 0:
+            return False
+        dev, st = self._ds(x)
+        dx = _desc(x)
+        self._check(self.lib.b200seg_head_fwd(C.byref(dx), w.data_ptr(), _p(bias), logits.data_ptr(), probs.data_ptr(),
+                                              nc, dev, st))
+        return True
+
+    def head_bwd(self, x, dlogits, w, dx, dw, db):
+        nc = dlogits.shape[-1]
+        if not self.lib.b200seg_head_bwd_supported(x.shape[-1], nc):
+            return False
+        dev, st = self._ds(x)
+        d1, d2 = _desc(x), _desc(dx)
+        self._check(self.lib.b200seg_head_bwd(C.byref(d1), dlogits.data_ptr(), w.data_ptr(), C.byref(d2),
+                                              dw.data_ptr(), db.data_ptr(), nc, dev, st))
+        return True
 
     def loss_partials(self, logits, labels, gamma, alpha_f, part):
         dev, st = self._ds(logits)

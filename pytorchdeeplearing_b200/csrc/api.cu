@@ -25,6 +25,17 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
             double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
 int conv_tc_init(int device);
 int conv_tc_channels_ok(int kind, int cin, int cout);
+int smallcin_conv_supported(int kind, const b200seg_tensor* x, const b200seg_tensor* y, const b200seg_tensor* addend);
+int smallcin_conv(int kind, int dims, const b200seg_tensor* x, const void* w, int w_dtype, const float* bias,
+                  const b200seg_tensor* y, double* stats, int device, cudaStream_t st);
+int smallcin_wgrad_supported(int kind, const b200seg_tensor* a, const b200seg_tensor* b);
+int smallcin_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+                   cudaStream_t st);
+int head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* logits, float* probs, int nc,
+             int device, cudaStream_t st);
+int head_bwd_supported(const b200seg_tensor* x, int nc);
+int head_bwd(const b200seg_tensor* x, const float* dl, const float* w, const b200seg_tensor* dx, float* dw, float* db,
+             int nc, int device, cudaStream_t st);
 int wgrad_tc_supported(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b);
 int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
              cudaStream_t st);
@@ -110,6 +121,9 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
     return conv_tc(kind, dims, x, wpk, bias, y, stats, addend, device, ST(stream));
   B200_CHECK_ARG(w_dtype != B200SEG_BF16_TC,
                  "b200seg_conv: B200SEG_BF16_TC weights need bf16, 16-byte aligned activations of a supported shape");
+  if (smallcin_conv_supported(kind, x, y, addend) &&
+      (w_dtype == B200SEG_F32 ? (x->dtype == B200SEG_F32 && y->dtype == B200SEG_F32) : y->dtype == B200SEG_BF16))
+    return smallcin_conv(kind, dims, x, wpk, w_dtype, bias, y, stats, device, ST(stream));
   return conv_generic(kind, dims, x, wpk, w_dtype, bias, y, stats, addend, ST(stream));
 }
 
@@ -131,6 +145,7 @@ int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_ten
     if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
     return wgrad_tc(kind, dims, a, b, dwp, device, ST(stream));
   }
+  if (smallcin_wgrad_supported(kind, a, b)) return smallcin_wgrad(kind, dims, a, b, dwp, device, ST(stream));
   return wgrad_generic(kind, dims, a, b, dwp, device, ST(stream));
 }
 
@@ -207,6 +222,29 @@ int b200seg_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* g_out, const
   B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_pool_bwd: dims must be 2 or 3");
   B200_DEVICE(device);
   return ew_pool_bwd(x, g_out, addend, g_x, dims, device, ST(stream));
+}
+
+int b200seg_head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* logits, float* probs, int nc,
+                     int device, b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  B200_CHECK_ARG(w && logits && probs, "b200seg_head_fwd: null argument");
+  B200_DEVICE(device);
+  return head_fwd(x, w, bias, logits, probs, nc, device, ST(stream));
+}
+
+int b200seg_head_bwd_supported(int cin, int nc) {
+  b200seg_tensor t;
+  t.c = cin;
+  return head_bwd_supported(&t, nc);
+}
+
+int b200seg_head_bwd(const b200seg_tensor* x, const float* dlogits, const float* w, const b200seg_tensor* dx,
+                     float* dw, float* db, int nc, int device, b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  REQ_TENSOR(dx, "dx");
+  B200_CHECK_ARG(dlogits && w && dw && db, "b200seg_head_bwd: null argument");
+  B200_DEVICE(device);
+  return head_bwd(x, dlogits, w, dx, dw, db, nc, device, ST(stream));
 }
 
 int b200seg_head_probs(const float* logits, float* probs, int64_t nvox_, int C, int device, b200seg_stream stream) {

@@ -47,14 +47,17 @@ struct TcArgs {
   const float* bias;
   double* stats;          // [N][Cout][2] or null
   long long yld, ald;
-  int N, D, H, W;         // output (= input) spatial dims
+  int N, D, H, W;         // tile-space dims: output dims (gather kinds) or input dims (UP)
   int Cin, Cout;
   int kd, kh, kw, pd, ph, pw;
+  int sd, sh, sw;         // gather strides (2 for the k2s2 down conv)
+  int up, ud, uh, uw;     // UP: columns are (tap, cout), depth-to-space store with these factors
+  int Ntile, ngroups;     // MMA N (columns per accumulator) and number of column groups per voxel tile
   int bw, bh, bd;         // M-tile box, bw*bh*bd == 128
   int tw, th, td;         // tiles per dim
   int ntiles;             // N * td * th * tw
   int nstages;
-  int tmem_cols;          // power of two >= 2*Cout (>= 32)
+  int tmem_cols;          // power of two >= 2*Ntile (>= 32)
 };
 
 constexpr int kMaxStages = 8;
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   constexpr uint32_t A_BYTES = 128u * SWZ;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t b_bytes_real = (uint32_t)p.Cout * SWZ;
+  const uint32_t b_bytes_real = (uint32_t)p.Ntile * SWZ;
   const uint32_t B_BYTES = (b_bytes_real + 1023u) & ~1023u;
   const uint32_t STAGE = A_BYTES + B_BYTES;
   uint8_t* tail = smem + (size_t)p.nstages * STAGE;
@@ -81,9 +84,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_per_cta = (p.ntiles + gridDim.x - 1) / gridDim.x;
-  const int tile_begin = blockIdx.x * tiles_per_cta;
-  const int tile_end = min(p.ntiles, tile_begin + tiles_per_cta);
+  // work item = (voxel tile, column group); consecutive items of a CTA share the voxel tile
+  const int nitems = p.ntiles * p.ngroups;
+  const int items_per_cta = (nitems + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * items_per_cta;
+  const int tile_end = min(nitems, tile_begin + items_per_cta);
   const int taps = p.kd * p.kh * p.kw;
   const int cblocks = p.Cin / BKC;
   const int kblocks = taps * cblocks;
@@ -114,13 +119,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     // ===================================================== TMA producer
     if (elect_one()) {
       uint32_t it = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        int t = tile;
+      for (int item = tile_begin; item < tile_end; ++item) {
+        int t = item / p.ngroups;
+        const int ng = item - t * p.ngroups;
         const int iw = t % p.tw; t /= p.tw;
         const int ih = t % p.th; t /= p.th;
         const int id = t % p.td;
         const int n = t / p.td;
-        const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd;
+        const int w0 = iw * p.bw * p.sw, h0 = ih * p.bh * p.sh, d0 = id * p.bd * p.sd;
         for (int tap = 0; tap < taps; ++tap) {
           const int kw_ = tap % p.kw;
           const int kh_ = (tap / p.kw) % p.kh;
@@ -132,22 +138,22 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
             uint8_t* sa = smem + (size_t)s * STAGE;
             mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
             tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
-            tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, tap * p.Cout);
+            tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);
     uint32_t it = 0;
     int local = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
+    for (int item = tile_begin; item < tile_end; ++item, ++local) {
       const uint32_t as = local & 1;
       const uint32_t aph = (local >> 1) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout;
+      const uint32_t tacc = tmem_base + as * (uint32_t)p.Ntile;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const uint32_t s = it % p.nstages;
         const uint32_t ph = (it / p.nstages) & 1u;
@@ -189,8 +195,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
-      int t = tile;
+    for (int item = tile_begin; item < tile_end; ++item, ++local) {
+      int t = item / p.ngroups;
+      const int ng = item - t * p.ngroups;
       const int iw = t % p.tw; t /= p.tw;
       const int ih = t % p.th; t /= p.th;
       const int id = t % p.td;
@@ -206,10 +213,21 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       const uint32_t aph = (local >> 1) & 1u;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+      const uint32_t tacc = tmem_base + as * (uint32_t)p.Ntile + ((uint32_t)(q * 32) << 16);
+      for (int cc = 0; cc < p.Ntile; cc += 16) {
         float v[16];
-        tmem_ld16(tacc + (uint32_t)c0, v);
+        tmem_ld16(tacc + (uint32_t)cc, v);
+        // channel block of this 16-column chunk (UP: columns are (tap, cout))
+        int c0 = cc;
+        long long ovox = vox;
+        if (p.up) {
+          const int col = ng * p.Ntile + cc;
+          const int tp = col / p.Cout;
+          c0 = col - tp * p.Cout;
+          const int fc = tp % p.uw, fb = (tp / p.uw) % p.uh, fa = tp / (p.uw * p.uh);
+          ovox = (((long long)n * (p.D * p.ud) + (od * p.ud + fa)) * (p.H * p.uh) + (oh * p.uh + fb)) * (p.W * p.uw) +
+                 (ow * p.uw + fc);
+        }
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
@@ -247,13 +265,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         if (valid) {
           if (p.addend != nullptr) {
             float r[16];
-            load8(p.addend + vox * p.ald + c0, r);
-            load8(p.addend + vox * p.ald + c0 + 8, r + 8);
+            load8(p.addend + ovox * p.ald + c0, r);
+            load8(p.addend + ovox * p.ald + c0 + 8, r + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += r[j];
           }
-          store8(p.y + vox * p.yld + c0, v);
-          store8(p.y + vox * p.yld + c0 + 8, v + 8);
+          store8(p.y + ovox * p.yld + c0, v);
+          store8(p.y + ovox * p.yld + c0 + 8, v + 8);
         }
       }
       tc_fence_before();
@@ -284,22 +302,29 @@ static int pick_bkc(int cin) {
 }
 
 int conv_tc_channels_ok(int kind, int cin, int cout) {
-  if (kind != B200SEG_K3 && kind != B200SEG_K1) return 0;
+  if (kind < B200SEG_K3 || kind > B200SEG_UP) return 0;
   if (pick_bkc(cin) == 0) return 0;
   if (cout < 16 || cout > 256 || (cout % 16) != 0) return 0;
+  // transposed conv: the (tap, cout) columns are split into groups of <= 256 whole taps
+  if (kind == B200SEG_UP && (cout & (cout - 1)) != 0) return 0;
   return 1;
 }
 
 int conv_tc_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
                       const b200seg_tensor* addend) {
-  (void)dims;
   if (w_dtype != B200SEG_BF16_TC) return 0;
   if (!conv_tc_channels_ok(kind, x->c, y->c)) return 0;
   if (x->dtype != B200SEG_BF16 || y->dtype != B200SEG_BF16) return 0;
   if (addend && addend->dtype != B200SEG_BF16) return 0;
   if ((x->ld % 8) || (y->ld % 8) || !al16p(x->ptr) || !al16p(y->ptr)) return 0;
   if (addend && ((addend->ld % 8) || !al16p(addend->ptr))) return 0;
-  if (x->d != y->d || x->h != y->h || x->w != y->w) return 0;
+  ConvGeom g;
+  if (conv_geometry(kind, dims, &g) != 0) return 0;
+  if (g.up) {
+    if (y->d != x->d * g.ud || y->h != x->h * g.uh || y->w != x->w * g.uw) return 0;
+  } else {
+    if (x->d != y->d * g.sd || x->h != y->h * g.sh || x->w != y->w * g.sw) return 0;
+  }
   return 1;
 }
 
@@ -352,9 +377,15 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   p.stats = stats;
   p.yld = y->ld;
   p.ald = addend ? addend->ld : 0;
-  p.N = x->n; p.D = x->d; p.H = x->h; p.W = x->w;
+  p.N = x->n;
+  if (g.up) { p.D = x->d; p.H = x->h; p.W = x->w; } else { p.D = y->d; p.H = y->h; p.W = y->w; }
   p.Cin = x->c; p.Cout = y->c;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
+  p.sd = g.sd; p.sh = g.sh; p.sw = g.sw;
+  p.up = g.up; p.ud = g.ud; p.uh = g.uh; p.uw = g.uw;
+  const int ncols = g.up ? g.ud * g.uh * g.uw * p.Cout : p.Cout;
+  p.Ntile = ncols > 256 ? 256 : ncols;
+  p.ngroups = ncols / p.Ntile;
   tc_pick_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd);
   p.tw = (p.W + p.bw - 1) / p.bw;
   p.th = (p.H + p.bh - 1) / p.bh;
@@ -363,7 +394,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const int bkc = pick_bkc(p.Cin);
   const uint32_t swz = bkc * 2;
   const uint32_t a_bytes = 128u * swz;
-  const uint32_t b_bytes = (((uint32_t)p.Cout * swz) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (((uint32_t)p.Ntile * swz) + 1023u) & ~1023u;
   const uint32_t stage = a_bytes + b_bytes;
   const uint32_t tail = (2 * kMaxStages + 4) * 8 + 16 + 2 * p.Cout * 4;
   const int maxsm = g_smem_optin[device] > 0 ? g_smem_optin[device] : 227 * 1024;
@@ -372,7 +403,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   B200_CHECK_ARG(nst >= 2, "conv_tc: tile does not fit in shared memory (Cin=%d Cout=%d)", p.Cin, p.Cout);
   p.nstages = nst;
   int cols = 32;
-  while (cols < 2 * p.Cout) cols *= 2;
+  while (cols < 2 * p.Ntile) cols *= 2;
   p.tmem_cols = cols;
   const size_t smem_bytes = 1024 + (size_t)nst * stage + tail + 128;
 
@@ -381,21 +412,23 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const CUtensorMapSwizzle sw = bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                           : (bkc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   {
-    cuuint64_t dims5[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
-    cuuint64_t strides[4] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->ld * 2 * p.W, (cuuint64_t)x->ld * 2 * p.W * p.H,
-                             (cuuint64_t)x->ld * 2 * p.W * p.H * p.D};
-    cuuint32_t box[5] = {(cuuint32_t)bkc, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    cuuint64_t dims5[5] = {(cuuint64_t)p.Cin, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->d, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)x->ld * 2, (cuuint64_t)x->ld * 2 * x->w, (cuuint64_t)x->ld * 2 * x->w * x->h,
+                             (cuuint64_t)x->ld * 2 * x->w * x->h * x->d};
+    // strided gather (k2s2 down conv): the box spans s*b positions traversed with element stride s
+    cuuint32_t box[5] = {(cuuint32_t)bkc, (cuuint32_t)(p.bw * p.sw), (cuuint32_t)(p.bh * p.sh),
+                         (cuuint32_t)(p.bd * p.sd), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)p.sw, (cuuint32_t)p.sh, (cuuint32_t)p.sd, 1};
     CUresult r = g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, dims5, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
-    const int taps = g.kd * g.kh * g.kw;
-    cuuint64_t dims2[2] = {(cuuint64_t)p.Cin, (cuuint64_t)taps * p.Cout};
+    const int rows = g.up ? ncols : g.kd * g.kh * g.kw * p.Cout;
+    cuuint64_t dims2[2] = {(cuuint64_t)p.Cin, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bkc, (cuuint32_t)p.Cout};
+    cuuint32_t box[2] = {(cuuint32_t)bkc, (cuuint32_t)p.Ntile};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpk), dims2, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -403,7 +436,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
     B200_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
   int grid = num_sms(device);
-  if (grid > p.ntiles) grid = p.ntiles;
+  if (grid > p.ntiles * p.ngroups) grid = p.ntiles * p.ngroups;
   if (bkc == 64) conv_tc_kernel<64><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
   else if (bkc == 32) conv_tc_kernel<32><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
   else conv_tc_kernel<16><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);

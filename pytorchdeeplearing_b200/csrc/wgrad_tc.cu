@@ -23,7 +23,7 @@ struct WgArgs {
   float* dwp;
   int N, D, H, W;
   int Ka, Kb, Rtot;          // rows per tap, columns, taps*Ka
-  int kd, kh, kw, pd, ph, pw;
+  int kd, kh, kw, pd, ph, pw, sd, sh, sw;
   int bw, bh, bd, tw, th, td, ntiles;
   int CA, CB;                // channels per A / B sub-tile (<= 64)
   int mblocks_total, mb_per_cta;
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             const int kw_ = tap % p.kw;
             const int kh_ = (tap / p.kw) % p.kh;
             const int kd_ = tap / (p.kw * p.kh);
-            tma_load_5d(&tmA, sa + (size_t)j * A_SUB, &full[s], ch, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
+            tma_load_5d(&tmA, sa + (size_t)j * A_SUB, &full[s], ch, w0 * p.sw + kw_ - p.pw, h0 * p.sh + kh_ - p.ph,
+                        d0 * p.sd + kd_ - p.pd, n);
           }
           for (uint32_t j = 0; j < nbsub; ++j)
             tma_load_5d(&tmB, sa + A_BYTES + (size_t)j * B_SUB, &full[s], (int)j * p.CB, w0, h0, d0, n);
@@ -194,17 +195,18 @@ int wgrad_tc_init(int device, int maxsm) {
 }
 
 int wgrad_tc_supported(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b) {
-  (void)dims;
-  if (kind != B200SEG_K3 && kind != B200SEG_K1) return 0;
+  ConvGeom g;
+  if (conv_geometry(kind, dims, &g) != 0 || g.up) return 0;
   if (a->dtype != B200SEG_BF16 || b->dtype != B200SEG_BF16) return 0;
   if (sub_channels(a->c) == 0 || sub_channels(b->c) == 0) return 0;
   if (a->c > 256 || b->c > 256) return 0;
   if ((a->ld % 8) || (b->ld % 8) || !al16w(a->ptr) || !al16w(b->ptr)) return 0;
-  if (a->n != b->n || a->d != b->d || a->h != b->h || a->w != b->w) return 0;
+  if (a->n != b->n || a->d != b->d * g.sd || a->h != b->h * g.sh || a->w != b->w * g.sw) return 0;
   return 1;
 }
 
-static int encode_box_map(CUtensorMap* tm, const b200seg_tensor* t, int cbox, int bw, int bh, int bd) {
+static int encode_box_map(CUtensorMap* tm, const b200seg_tensor* t, int cbox, int bw, int bh, int bd, int sw_ = 1,
+                          int sh_ = 1, int sd_ = 1) {
   EncodeTiledFn enc = tc_encode_fn();
   if (!enc) return B200SEG_ECUDA;
   const CUtensorMapSwizzle sw = cbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -212,8 +214,8 @@ static int encode_box_map(CUtensorMap* tm, const b200seg_tensor* t, int cbox, in
   cuuint64_t dims5[5] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->d, (cuuint64_t)t->n};
   cuuint64_t strides[4] = {(cuuint64_t)t->ld * 2, (cuuint64_t)t->ld * 2 * t->w, (cuuint64_t)t->ld * 2 * t->w * t->h,
                            (cuuint64_t)t->ld * 2 * t->w * t->h * t->d};
-  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)(bw * sw_), (cuuint32_t)(bh * sh_), (cuuint32_t)(bd * sd_), 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)sw_, (cuuint32_t)sh_, (cuuint32_t)sd_, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t->ptr, dims5, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -230,6 +232,7 @@ int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* 
   p.N = b->n; p.D = b->d; p.H = b->h; p.W = b->w;
   p.Ka = a->c; p.Kb = b->c;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
+  p.sd = g.sd; p.sh = g.sh; p.sw = g.sw;
   p.Rtot = g.kd * g.kh * g.kw * p.Ka;
   tc_pick_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd);
   p.tw = (p.W + p.bw - 1) / p.bw;
@@ -256,7 +259,7 @@ int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* 
   p.nstages = nst;
   const size_t smem_bytes = 1024 + (size_t)nst * stage + tail + 128;
   CUtensorMap tmA, tmB;
-  int rc = encode_box_map(&tmA, a, p.CA, p.bw, p.bh, p.bd);
+  int rc = encode_box_map(&tmA, a, p.CA, p.bw, p.bh, p.bd, g.sw, g.sh, g.sd);
   if (rc != B200SEG_OK) return rc;
   rc = encode_box_map(&tmB, b, p.CB, p.bw, p.bh, p.bd);
   if (rc != B200SEG_OK) return rc;

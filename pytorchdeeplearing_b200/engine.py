@@ -112,6 +112,22 @@ class Engine:
         self.layers.append(L)
         return L
 
+    def head(self, wname: str, bname: str, x: Tensor, sp0, ncls: int) -> Tuple[Layer, Tensor, Tensor]:
+        """OutputTransition3d / UNet head: 1x1 conv to the classes + sigmoid/softmax (VNet3d.py:90-99)."""
+        logits = self.new(x, sp0, ncls, dtype=torch.float32)
+        probs = torch.empty_like(logits)
+        Lh = Layer(K1, wname, bname, None, x=x, y=logits)
+        if not self.be.head_fwd(x, self.P[wname], self.P[bname], logits, probs):
+            self.conv_raw(K1, wname, bname, x, logits)
+            self.be.head_probs(logits, probs)
+        return Lh, logits, probs
+
+    def head_backward(self, Lh: Layer, g_logits: Tensor) -> Tensor:
+        dx = torch.empty(Lh.x.shape, dtype=self.T, device=g_logits.device)
+        if self.be.head_bwd(Lh.x, g_logits, self.P[Lh.wname], dx, self._grad_view(Lh.wname), self._grad_view(Lh.bname)):
+            return dx
+        return self.bwd_layer(Lh, g_logits, True, dx_out=dx)
+
     def act(self, L: Layer, out: Tensor, L2: Optional[Layer] = None, res: Optional[Tensor] = None) -> Tensor:
         self.be.apply(L.y, L.coef, L2.y if L2 is not None else None, L2.coef if L2 is not None else None, res, out)
         return out
@@ -240,11 +256,7 @@ class Engine:
 
         # ---- OutputTransition3d (VNet3d.py:90-99)
         ncls = P["out_tr.conv.weight"].shape[0]
-        logits = self.new(x, sp0, ncls, dtype=torch.float32)
-        Lh = Layer(K1, "out_tr.conv.weight", "out_tr.conv.bias", None, x=out, y=logits)
-        self.conv_raw(K1, Lh.wname, Lh.bname, out, logits)
-        probs = torch.empty_like(logits)
-        self.be.head_probs(logits, probs)
+        Lh, logits, probs = self.head("out_tr.conv.weight", "out_tr.conv.bias", out, sp0, ncls)
         sv["head"] = Lh
         return logits.permute(0, 4, 1, 2, 3), probs.permute(0, 4, 1, 2, 3)
 
@@ -253,8 +265,7 @@ class Engine:
         channels-last).  Returns the flat fp32 bucket; ``self.grads`` holds the views."""
         sv = self.saved
         flat = self.alloc_grads(g_logits.device)
-        Lh: Layer = sv["head"]
-        g = self.bwd_layer(Lh, g_logits, True)
+        g = self.head_backward(sv["head"], g_logits)
         gskip: List[Optional[Tensor]] = [None] * 4
         for i, name in zip((0, 1, 2, 3), ["up_tr32", "up_tr64", "up_tr128", "up_tr256"]):
             Lu, Lc, ops = sv[name]
@@ -326,11 +337,7 @@ class Engine:
             sv[f"upconv{k}"] = Lu
             h = block(f"decoder{k}", f"dec{k}", cats[i], sps[i], ch[i], self.new(x, sps[i], ch[i]))
         ncls = P["conv.weight"].shape[0]
-        logits = self.new(x, sp0, ncls, dtype=torch.float32)
-        Lh = Layer(K1, "conv.weight", "conv.bias", None, x=h, y=logits)
-        self.conv_raw(K1, Lh.wname, Lh.bname, h, logits)
-        probs = torch.empty_like(logits)
-        self.be.head_probs(logits, probs)
+        Lh, logits, probs = self.head("conv.weight", "conv.bias", h, sp0, ncls)
         sv["head"] = Lh
         if dims == 3:
             return logits.permute(0, 4, 1, 2, 3), probs.permute(0, 4, 1, 2, 3)
@@ -339,7 +346,7 @@ class Engine:
     def unet_backward(self, g_logits: Tensor) -> Tensor:
         sv = self.saved
         flat = self.alloc_grads(g_logits.device)
-        g = self.bwd_layer(sv["head"], g_logits, True)
+        g = self.head_backward(sv["head"], g_logits)
         genc: List[Optional[Tensor]] = [None] * 4
         for i in (0, 1, 2, 3):
             k = i + 1

@@ -196,7 +196,7 @@ class EmuBackend:
         dy.copy_(out.to(dy.dtype))
 
     def colsum(self, dy, out):
-        out.copy_(dy.double().sum((0, 1, 2, 3)).float())
+        out += dy.double().sum((0, 1, 2, 3)).float()
 
     # ------------------------------------------------------------------ head + losses
     def head_probs(self, logits, probs):
@@ -204,6 +204,28 @@ class EmuBackend:
             probs.copy_(torch.sigmoid(logits))
         else:
             probs.copy_(torch.softmax(logits, dim=-1))
+
+    def head_fwd(self, x, w, bias, logits, probs):
+        nc = logits.shape[-1]
+        if nc > 8 or x.shape[-1] % 4 != 0:
+            return False
+        z = torch.einsum("ndhwk,ck->ndhwc", x.float(), w.reshape(nc, -1).float())
+        if bias is not None:
+            z = z + bias.float()
+        logits.copy_(z)
+        self.head_probs(logits, probs)
+        return True
+
+    def head_bwd(self, x, dlogits, w, dx, dw, db):
+        nc, cin = dlogits.shape[-1], x.shape[-1]
+        if nc > 4 or cin not in (16, 32):
+            return False
+        w2 = w.reshape(nc, cin).double()
+        g = dlogits.double()
+        dx.copy_(torch.einsum("ndhwc,ck->ndhwk", g, w2).to(dx.dtype))
+        dw += torch.einsum("ndhwc,ndhwk->ck", g, x.double()).reshape(dw.shape).float()
+        db += g.sum((0, 1, 2, 3)).float()
+        return True
 
     def loss_partials(self, logits, labels, gamma, alpha_f, part):
         """part (double): multi-class C>1: [I_c]*C, [P_c]*C, [Cnt_c]*C, sum_nll, sum_focal, V

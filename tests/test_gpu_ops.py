@@ -271,3 +271,30 @@ def test_head_and_losses(be, c):
             dz_c = torch.empty_like(z, device="cuda")
             be.loss_bwd(z.cuda(), t.cuda(), lc_e.cuda(), gs.cuda(), dz_c)
             assert (dz_c.cpu() - dz_e).abs().max() < 1e-6 * (1 + dz_e.abs().max()) + 3e-5 * dz_e.abs().max()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("nc,cin", [(1, 16), (2, 16), (4, 16), (3, 32), (8, 16)])
+def test_fused_head(be, dtype, nc, cin):
+    g = torch.Generator().manual_seed(6)
+    n, sp = 2, (3, 5, 8)
+    xbuf = rnd((n,) + sp + (cin + 16,), dtype, g)
+    x = xbuf[..., 8:8 + cin]
+    w = torch.randn(nc, cin, 1, 1, 1, generator=g) * 0.3
+    b = torch.randn(nc, generator=g) * 0.1
+    lo_e, pr_e = torch.empty((n,) + sp + (nc,)), torch.empty((n,) + sp + (nc,))
+    assert EMU.head_fwd(x, w, b, lo_e, pr_e)
+    lo_c, pr_c = torch.empty_like(lo_e, device="cuda"), torch.empty_like(pr_e, device="cuda")
+    assert be.head_fwd(x.cuda(), w.cuda(), b.cuda(), lo_c, pr_c)
+    assert rel(lo_c, lo_e) < 1e-5 and (pr_c.cpu() - pr_e).abs().max() < 1e-5
+    dl = torch.randn((n,) + sp + (nc,), generator=g)
+    dx_e = torch.empty((n,) + sp + (cin,), dtype=dtype)
+    dw_e, db_e = torch.zeros(nc, cin, 1, 1, 1), torch.zeros(nc)
+    ok = EMU.head_bwd(x, dl, w, dx_e, dw_e, db_e)
+    dx_c = torch.empty((n,) + sp + (cin,), dtype=dtype, device="cuda")
+    dw_c, db_c = torch.zeros(nc, cin, 1, 1, 1, device="cuda"), torch.zeros(nc, device="cuda")
+    okc = be.head_bwd(x.cuda(), dl.cuda(), w.cuda(), dx_c, dw_c, db_c)
+    assert bool(ok) == bool(okc)
+    if ok:
+        assert rel(dx_c, dx_e) < tol(dtype, 0.5)
+        assert rel(dw_c, dw_e) < 1e-5 and rel(db_c, db_e) < 1e-5
