@@ -4,7 +4,7 @@ forward and data-gradient forms, 3x3x3 / 3x3 / 1x1, ragged volumes (box overhang
 import pytest
 import torch
 
-from emu_backend import EmuBackend, K3, K1
+from emu_backend import EmuBackend, K3, K1, DOWN, UP
 
 pytestmark = pytest.mark.gpu
 EMU = EmuBackend()
@@ -135,3 +135,77 @@ def test_tc_wgrad_matches_emulation(be, kind, dims, n, sp, ka, kb):
     be.wgrad(kind, dims, a.cuda(), b.cuda(), dw_c)
     torch.cuda.synchronize()
     assert rel(dw_c, 2 * dw_e) < 2e-5
+
+
+RESAMPLE_CASES = [
+    # kind, dims, n, INPUT spatial, cin, cout
+    (DOWN, 3, 2, (8, 16, 16), 16, 32),
+    (DOWN, 3, 1, (8, 8, 16), 64, 128),
+    (DOWN, 3, 1, (4, 4, 4), 128, 256),
+    (DOWN, 3, 2, (12, 12, 12), 32, 64),       # ragged
+    (DOWN, 2, 2, (1, 32, 48), 16, 32),
+    (UP, 3, 2, (4, 8, 8), 32, 16),
+    (UP, 3, 1, (4, 4, 8), 128, 64),           # 8*64 = 512 columns -> 2 column groups
+    (UP, 3, 1, (2, 2, 2), 256, 128),          # 4 column groups
+    (UP, 3, 2, (6, 6, 6), 64, 32),            # ragged
+    (UP, 2, 2, (1, 16, 24), 32, 16),
+    (UP, 2, 1, (1, 8, 8), 256, 128),
+]
+
+
+def _out_sp(kind, dims, sp):
+    if kind == DOWN:
+        return (sp[0] // 2 if dims == 3 else 1, sp[1] // 2, sp[2] // 2)
+    return (sp[0] * 2 if dims == 3 else 1, sp[1] * 2, sp[2] * 2)
+
+
+@pytest.mark.parametrize("kind,dims,n,sp,cin,cout", RESAMPLE_CASES)
+def test_tc_down_up_forward_dgrad_wgrad(be, kind, dims, n, sp, cin, cout):
+    """k2s2 conv / transposed conv on the tcgen05 path: forward, data gradient (the opposite form) and
+    weight gradient (strided TMA gather), all against the emulation."""
+    g = torch.Generator().manual_seed(11)
+    dt = torch.bfloat16
+    kk = (2,) * dims
+    wshape = ((cin, cout) if kind == UP else (cout, cin)) + kk
+    w = torch.randn(wshape, generator=g) * (2.0 / (cin * 2 ** dims)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    osp = _out_sp(kind, dims, sp)
+    xbuf = torch.randn((n,) + sp + (cin + 16,), generator=g).to(dt)
+    x = xbuf[..., 8:8 + cin]
+    # ---- forward (+ stats)
+    wp_c = be.pack_weight(w.cuda(), kind, "fwd", dt, dims)
+    assert wp_c.code == 2
+    wp_e = EMU.pack_weight(w, kind, "fwd", dt, dims)
+    y_e = torch.zeros((n,) + osp + (cout,), dtype=dt)
+    st_e = torch.zeros(n, cout, 2, dtype=torch.float64)
+    EMU.conv(kind, dims, x, wp_e, bias, y_e, st_e, None)
+    ybuf = torch.zeros((n,) + osp + (cout + 32,), dtype=dt, device="cuda")
+    y_c = ybuf[..., 16:16 + cout]
+    st_c = torch.zeros(n, cout, 2, dtype=torch.float64, device="cuda")
+    be.conv(kind, dims, x.cuda(), wp_c, bias.cuda(), y_c, st_c, None)
+    torch.cuda.synchronize()
+    assert rel(y_c, y_e) < 6e-3, rel(y_c, y_e)
+    assert rel(st_c, st_e) < 1e-4
+    assert float(ybuf[..., :16].abs().max()) == 0 and float(ybuf[..., 16 + cout:].abs().max()) == 0
+    # ---- data gradient (+ addend)
+    dy = torch.randn((n,) + osp + (cout,), generator=g).to(dt)
+    add = torch.randn((n,) + sp + (cin,), generator=g).to(dt)
+    DK = UP if kind == DOWN else DOWN
+    wd_c = be.pack_weight(w.cuda(), kind, "dgrad", dt, dims)
+    assert wd_c.code == 2
+    wd_e = EMU.pack_weight(w, kind, "dgrad", dt, dims)
+    dx_e = torch.zeros((n,) + sp + (cin,), dtype=dt)
+    EMU.conv(DK, dims, dy, wd_e, None, dx_e, None, add)
+    dx_c = torch.zeros((n,) + sp + (cin,), dtype=dt, device="cuda")
+    be.conv(DK, dims, dy.cuda(), wd_c, None, dx_c, None, add.cuda())
+    torch.cuda.synchronize()
+    assert rel(dx_c, dx_e) < 6e-3, rel(dx_c, dx_e)
+    # ---- weight gradient (DOWN-type gather on the fine side)
+    taps = 2 ** dims
+    fine, coarse = (x, dy) if kind == DOWN else (dy, x)
+    dw_e = torch.zeros(taps, fine.shape[-1], coarse.shape[-1])
+    EMU.wgrad(DOWN, dims, fine, coarse, dw_e)
+    dw_c = torch.zeros(taps, fine.shape[-1], coarse.shape[-1], device="cuda")
+    be.wgrad(DOWN, dims, fine.cuda().contiguous(), coarse.cuda().contiguous(), dw_c)
+    torch.cuda.synchronize()
+    assert rel(dw_c, dw_e) < 2e-5, rel(dw_c, dw_e)
