@@ -134,8 +134,8 @@ class TimedBackend:
     def _describe(name, a):
         if name == "conv":
             kind, dims, x, wpk, bias, y = a[:6]
-            tc = getattr(wpk, "code", 0) == 2
-            return f"conv[k{kind}{'/tcgen05' if tc else '/ffma'}] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
+            path = {2: "/tcgen05", 3: "/tcgen05-halo"}.get(getattr(wpk, "code", 0), "/cuda-core")
+            return f"conv[k{kind}{path}] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
         if name == "wgrad":
             kind, dims, x, dy = a[:4]
             return f"wgrad[k{kind}] {x.shape[-1]}x{dy.shape[-1]}@{tuple(dy.shape[1:4])}"

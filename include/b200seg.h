@@ -36,6 +36,7 @@ extern "C" {
 #define B200SEG_F32 0
 #define B200SEG_BF16 1
 #define B200SEG_BF16_TC 2 /* weights only: bf16 packed [tap][N][K] (K-major) for the tcgen05/TMA conv path */
+#define B200SEG_BF16_HALO 3 /* weights only: bf16 packed [tap][K/8][N][8] (smem image of the halo-staged 3x3x3 path) */
 
 /* conv kinds */
 #define B200SEG_K3 0    /* 3x3x3 (dims==3) or 1x3x3 (dims==2), stride 1, zero pad 1 */
@@ -88,6 +89,10 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
  * B200SEG_BF16_TC weights ([tap][Cout][Cin] for the forward form, [tap'][Cin][Cout], taps flipped, for the
  * data-gradient form); 0 -> pack [tap][K][N] and use the CUDA-core path. */
 int b200seg_conv_tc_eligible(int kind, int cin, int cout);
+/* 1 if (kind, Cin -> Cout) can run on the halo-staged tcgen05 kernel (3x3x3 / 3x3, 16/32 channels) given
+ * B200SEG_BF16_HALO weights; meant for the full-resolution layers (each input voxel is staged once in shared
+ * memory instead of once per tap). */
+int b200seg_conv_halo_eligible(int kind, int cin, int cout);
 
 /* weight-gradient half of aten::convolution_backward:
  *   dwp[t][ka][kb] += sum_{n,o} a[n, o*s + t - p, ka] * b[n, o, kb]      (fp32, caller zero-fills)

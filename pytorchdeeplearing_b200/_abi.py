@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 K3, K1, DOWN, UP = 0, 1, 2, 3
-F32, BF16, BF16_TC = 0, 1, 2
+F32, BF16, BF16_TC, BF16_HALO = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200seg.so")
@@ -36,6 +36,7 @@ _SIGNATURES = {
     "b200seg_unpack_wgrad": ([_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp], C.c_int),
     "b200seg_conv": ([_i, _i, _PT, _vp, _i, _vp, _PT, _vp, _PT, _i, _vp], C.c_int),
     "b200seg_conv_tc_eligible": ([_i, _i, _i], C.c_int),
+    "b200seg_conv_halo_eligible": ([_i, _i, _i], C.c_int),
     "b200seg_wgrad": ([_i, _i, _PT, _PT, _vp, _i, _vp], C.c_int),
     "b200seg_gn_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_apply": ([_PT, _vp, _PT, _vp, _PT, _PT, _i, _vp], C.c_int),
@@ -138,6 +139,8 @@ class CudaBackend:
         self._inited = set()
         # B200SEG_DISABLE_TC=1 forces every conv onto the CUDA-core implicit-GEMM kernels (debug / A-B timing)
         self.use_tc = os.environ.get("B200SEG_DISABLE_TC", "0") != "1"
+        self.use_halo = os.environ.get("B200SEG_DISABLE_HALO", "0") != "1"
+        self.halo_min_vox = int(os.environ.get("B200SEG_HALO_MIN_VOX", str(128 * 128)))
         self.launch_count = 0      # kernels launched through the C ABI (one per successful entry-point call)
 
     # ------------------------------------------------------------------ plumbing
@@ -155,13 +158,29 @@ class CudaBackend:
         self.launch_count += 1
 
     # ------------------------------------------------------------------ weights
-    def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True):
+    def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True, vox=None):
+        """``vox``: voxels per sample of the layer's output (lets the backend pick the halo-staged kernel for the
+        full-resolution 16/32-channel layers)."""
         a, b = w.shape[0], w.shape[1]
         t = w.numel() // (a * b)
         dev, st = self._ds(w)
         od = F32 if dtype == torch.float32 else BF16
         code = od
         tc = False
+        if (allow_tc and self.use_tc and self.use_halo and dtype == torch.bfloat16 and kind == K3
+                and vox is not None and vox >= self.halo_min_vox):
+            cin, cout = (b, a) if which == "fwd" else (a, b)
+            if self.lib.b200seg_conv_halo_eligible(kind, cin, cout):
+                if which == "fwd":      # [t][ci/8][co][ci%8]
+                    out = torch.empty((t, b // 8, a, 8), dtype=dtype, device=w.device)
+                    args = (t, b // 8, a, 8, 1, 8 * t, b * t, t, 0)
+                else:                   # [T-1-t][co/8][ci][co%8]
+                    out = torch.empty((t, a // 8, b, 8), dtype=dtype, device=w.device)
+                    args = (t, a // 8, b, 8, 1, 8 * b * t, t, b * t, 1)
+                T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
+                self._check(self.lib.b200seg_pack_weight(w.data_ptr(), out.data_ptr(), od, T, K, N2, N1, s_t, s_k,
+                                                         s_n2, s_n1, flip, dev, st))
+                return PackedWeight(out, BF16_HALO, w, kind, which, dims)
         if allow_tc and self.use_tc and dtype == torch.bfloat16:
             # (kind, Cin, Cout) of the op that will consume the packed operand
             if which == "fwd":
@@ -213,7 +232,7 @@ class CudaBackend:
     # ------------------------------------------------------------------ conv family
     def conv(self, kind, dims, x, wpk, bias, y, stats, addend):
         dev, st = self._ds(x)
-        if wpk.code == BF16_TC and not (x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16):
+        if wpk.code in (BF16_TC, BF16_HALO) and not (x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16):
             # tcgen05 path needs bf16 activations on both sides (e.g. a 16-channel fp32 network input)
             wpk = self.pack_weight(wpk.src, wpk.kind, wpk.which, torch.bfloat16, wpk.dims, allow_tc=False)
         dx, dy, da = _desc(x), _desc(y), _desc(addend)

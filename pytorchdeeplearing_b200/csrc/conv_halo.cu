@@ -1,0 +1,377 @@
+// Halo-staged tcgen05 convolution for the full-resolution 16/32-channel 3x3(x3) layers (sm_100a, bf16).
+//
+// conv_tc.cu loads one shifted activation box per tap through TMA: 27 L2->smem transfers of the same
+// voxels per output tile, which makes the 16/32-channel layers (80 % of the network's bytes) L2-bound.
+// This kernel stages each input d-slice ONCE in shared memory and lets the 27 taps read shifted VIEWS of it:
+//   * a CTA owns an (8 wide x 16 high) output column and marches along d; a ring of input slices
+//     (18 x 10 voxels each, one-voxel halo, zero filled = conv padding) lives in smem, so each input voxel
+//     is fetched ~1.4x instead of 27x;
+//   * slices are stored channel-planar, [C/8 planes][18][10][8 ch], i.e. every voxel contributes one 16-byte
+//     K-chunk per plane and 8 consecutive voxels along w form one UMMA core matrix (8 rows x 16 B).  In the
+//     no-swizzle K-major canonical layout the 16 core-matrix rows of the M = 128 tile are then a constant
+//     SBO = 160 B (one halo row) apart and the two K-chunks LBO = one plane apart, for EVERY tap: the tap only
+//     moves the descriptor start address by (kh*10 + kw)*16 B inside the slice selected by kd;
+//   * the packed weights of all taps stay resident in smem for the CTA's lifetime;
+//   * loader warps move global -> registers -> smem with 128-bit accesses (this is where norm-on-load will be
+//     fused); MMA issue, TMEM double buffering and the epilogue (bias, GroupNorm statistics, residual
+//     addend, bf16 NDHWC stores) follow conv_tc.cu.
+// Warp roles (288 threads): warp 0 MMA issuer + TMEM allocator, warps 1-4 epilogue, warps 5-8 loaders.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace b200seg {
+
+constexpr int HT_W = 8, HT_H = 16;            // output tile (w, h); M = 128 rows = (hh, ww)
+constexpr int HP_W = HT_W + 2, HP_H = HT_H + 2;
+constexpr int kHaloMaxSlices = 8;
+
+struct HaloArgs {
+  const bf16* x;
+  const bf16* w;          // packed [tap][Cin/8][Cout][8]
+  bf16* y;
+  const bf16* addend;
+  const float* bias;
+  double* stats;
+  long long xld, yld, ald;
+  int N, D, H, W;
+  int Cin, Cout;
+  int kd;                 // 3 (3-D) or 1 (2-D)
+  int tw, th;             // tiles along w, h
+  int dchunk, ndchunks;   // output slices per work item, items along d
+  int nitems;             // N * th * tw * ndchunks
+  int nslices;            // ring size
+  int tmem_cols;
+  int swap_lbo_sbo;       // debug: swap the roles of the two descriptor strides
+};
+
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(288, 1) conv_halo_kernel(const HaloArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int CP = p.Cin / 8;                                  // 8-channel planes
+  const uint32_t PLANE = HP_H * HP_W * 16u;                  // bytes of one plane of one slice
+  const uint32_t SLICE = (uint32_t)CP * PLANE;
+  const int taps = p.kd * 9;
+  const uint32_t W_BYTES = (uint32_t)taps * p.Cin * p.Cout * 2u;
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + ((W_BYTES + 127u) & ~127u);
+  uint8_t* tail = s_ring + (size_t)p.nslices * SLICE;
+  tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* sempty = sfull + kHaloMaxSlices;
+  uint64_t* tfull = sempty + kHaloMaxSlices;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [2][Cout]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int items_per_cta = (p.nitems + gridDim.x - 1) / gridDim.x;
+  const int item_begin = blockIdx.x * items_per_cta;
+  const int item_end = min(p.nitems, item_begin + items_per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslices; ++s) {
+      mbar_init(&sfull[s], 4);      // one arrive per loader warp
+      mbar_init(&sempty[s], 1);     // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // resident weights: straight 16-byte copy of the pre-packed smem image
+  for (uint32_t i = threadIdx.x * 16u; i < W_BYTES; i += blockDim.x * 16u)
+    *reinterpret_cast<uint4*>(s_w + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + i);
+  for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int pd = p.kd / 2;
+
+  auto decode = [&](int item, int& n, int& h0, int& w0, int& d0, int& nd) {
+    int t = item;
+    const int dc = t % p.ndchunks; t /= p.ndchunks;
+    const int iw = t % p.tw; t /= p.tw;
+    const int ih = t % p.th;
+    n = t / p.th;
+    w0 = iw * HT_W;
+    h0 = ih * HT_H;
+    d0 = dc * p.dchunk;
+    nd = min(p.dchunk, p.D - d0);
+  };
+
+  if (warp == 0) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_lbo = p.swap_lbo_sbo ? HP_W * 16u : PLANE;
+    const uint32_t a_sbo = p.swap_lbo_sbo ? PLANE : HP_W * 16u;
+    const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.Cout * 16u;
+    const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)p.Cout * 16u : 128u;
+    const uint32_t ring_u32 = smem_u32(s_ring);
+    const uint32_t w_u32 = smem_u32(s_w);
+    const int kchunks = p.Cin / 16;
+    uint32_t gs = 0;   // slices consumed so far (ring position of the item's first slice)
+    uint32_t go = 0;   // output slice-tiles produced so far
+    for (int item = item_begin; item < item_end; ++item) {
+      int n, h0, w0, d0, nd;
+      decode(item, n, h0, w0, d0, nd);
+      const int nsl = nd + p.kd - 1;
+      for (int o = 0; o < nd; ++o, ++go) {
+        // input slices o .. o+kd-1 of this item must have landed
+        const int first_wait = (o == 0) ? 0 : p.kd - 1;
+        for (int k = first_wait; k < p.kd; ++k) {
+          const uint32_t sl = gs + o + k;
+          mbar_wait(&sfull[sl % p.nslices], (sl / p.nslices) & 1u);
+        }
+        const uint32_t as = go & 1u;
+        mbar_wait(&tempty[as], ((go >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout;
+          uint32_t first = 1;
+          for (int kd_ = 0; kd_ < p.kd; ++kd_) {
+            const uint32_t sl = gs + o + kd_;
+            const uint32_t sbase = ring_u32 + (sl % p.nslices) * SLICE;
+            for (int kh_ = 0; kh_ < 3; ++kh_)
+              for (int kw_ = 0; kw_ < 3; ++kw_) {
+                const int tap = (kd_ * 3 + kh_) * 3 + kw_;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                  const uint32_t a_addr = sbase + (uint32_t)(2 * kc) * PLANE + (uint32_t)(kh_ * HP_W + kw_) * 16u;
+                  const uint32_t b_addr = w_u32 + (uint32_t)((tap * kchunks + kc) * 2 * p.Cout) * 16u;
+                  umma_bf16(tacc, make_nosw_desc(a_addr, a_lbo, a_sbo), make_nosw_desc(b_addr, b_lbo, b_sbo), idesc,
+                            first ? 0u : 1u);
+                  first = 0;
+                }
+              }
+          }
+          umma_commit(&tfull[as]);
+          // input slice o is no longer needed; at the end of the item neither are the trailing kd-1
+          umma_commit(&sempty[(gs + o) % p.nslices]);
+          if (o == nd - 1)
+            for (int k = 1; k < p.kd; ++k) umma_commit(&sempty[(gs + o + k) % p.nslices]);
+        }
+        __syncwarp();
+      }
+      gs += (uint32_t)nsl;
+    }
+  } else if (warp >= 5) {
+    // ===================================================== loaders (128 threads)
+    const int lt = threadIdx.x - 160;
+    const int pieces = HP_H * HP_W * CP;
+    uint32_t gs = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      int n, h0, w0, d0, nd;
+      decode(item, n, h0, w0, d0, nd);
+      const int nsl = nd + p.kd - 1;
+      for (int i = 0; i < nsl; ++i) {
+        const uint32_t sl = gs + i;
+        const uint32_t slot = sl % p.nslices;
+        mbar_wait(&sempty[slot], ((sl / p.nslices) & 1u) ^ 1u);
+        const int d = d0 - pd + i;
+        const bool dok = (unsigned)d < (unsigned)p.D;
+        uint8_t* dst = s_ring + (size_t)slot * SLICE;
+        const bf16* src = p.x + (((long long)n * p.D + (dok ? d : 0)) * p.H) * p.W * p.xld;
+        for (int q = lt; q < pieces; q += 128) {
+          const int v = q / CP, plane = q - v * CP;
+          const int hh = v / HP_W, ww = v - hh * HP_W;
+          const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
+            val = *reinterpret_cast<const uint4*>(src + ((long long)h * p.W + w) * p.xld + plane * 8);
+          *reinterpret_cast<uint4*>(dst + (size_t)plane * PLANE + (size_t)v * 16) = val;
+        }
+        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfull[slot]);
+      }
+      gs += (uint32_t)nsl;
+    }
+  } else {
+    // ===================================================== epilogue warps 1..4
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rw = row % HT_W, rh = row / HT_W;
+    const int etid = (warp - 1) * 32 + lane;
+    uint32_t go = 0;
+    int cur_n = -1;
+    auto flush_stats = [&](int n) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.stats != nullptr && n >= 0) {
+        for (int i = etid; i < 2 * p.Cout; i += 128) {
+          const int which = i / p.Cout, c = i - which * p.Cout;
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, (double)s_stat[i]);
+          s_stat[i] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    for (int item = item_begin; item < item_end; ++item) {
+      int n, h0, w0, d0, nd;
+      decode(item, n, h0, w0, d0, nd);
+      if (n != cur_n) {
+        if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
+        cur_n = n;
+      }
+      const int oh = h0 + rh, ow = w0 + rw;
+      const bool valid = oh < p.H && ow < p.W;
+      for (int o = 0; o < nd; ++o, ++go) {
+        const long long vox = (((long long)n * p.D + (d0 + o)) * p.H + oh) * p.W + ow;
+        const uint32_t as = go & 1u;
+        mbar_wait(&tfull[as], (go >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          float v[16];
+          tmem_ld16(tacc + (uint32_t)c0, v);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+          }
+          if (p.stats != nullptr) {
+            float s[16], qq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              s[j] = valid ? v[j] : 0.f;
+              qq[j] = s[j] * s[j];
+            }
+#pragma unroll
+            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < half; ++j) {
+                const float keep_s = up ? s[j + half] : s[j];
+                const float send_s = up ? s[j] : s[j + half];
+                const float keep_q = up ? qq[j + half] : qq[j];
+                const float send_q = up ? qq[j] : qq[j + half];
+                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
+            }
+            s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+            qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+            if ((lane & 1) == 0) {
+              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              atomicAdd(&s_stat[c0 + col], s[0]);
+              atomicAdd(&s_stat[p.Cout + c0 + col], qq[0]);
+            }
+          }
+          if (valid) {
+            if (p.addend != nullptr) {
+              float r[16];
+              load8(p.addend + vox * p.ald + c0, r);
+              load8(p.addend + vox * p.ald + c0 + 8, r + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += r[j];
+            }
+            store8(p.y + vox * p.yld + c0, v);
+            store8(p.y + vox * p.yld + c0 + 8, v + 8);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+      }
+    }
+    if (p.stats != nullptr && cur_n >= 0) flush_stats(cur_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool al16h(const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
+
+int conv_halo_channels_ok(int kind, int cin, int cout) {
+  if (kind != B200SEG_K3) return 0;
+  if (cin != 16 && cin != 32) return 0;
+  if (cout != 16 && cout != 32) return 0;
+  return 1;
+}
+
+// the packed-weight image: [tap][Cin/8][Cout][8]  (== T taps, K = Cin/8 chunks, N2 = Cout, N1 = 8)
+int conv_halo_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                        const b200seg_tensor* addend) {
+  (void)dims;
+  if (w_dtype != B200SEG_BF16_HALO) return 0;
+  if (!conv_halo_channels_ok(kind, x->c, y->c)) return 0;
+  if (x->dtype != B200SEG_BF16 || y->dtype != B200SEG_BF16) return 0;
+  if (addend && addend->dtype != B200SEG_BF16) return 0;
+  if ((x->ld % 8) || (y->ld % 8) || !al16h(x->ptr) || !al16h(y->ptr)) return 0;
+  if (addend && ((addend->ld % 8) || !al16h(addend->ptr))) return 0;
+  if (x->d != y->d || x->h != y->h || x->w != y->w) return 0;
+  return 1;
+}
+
+static int g_halo_init[64] = {0};
+
+int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
+              double* stats, const b200seg_tensor* addend, int device, cudaStream_t st) {
+  (void)kind;
+  const int maxsm = tc_max_smem(device);
+  if (device >= 0 && device < 64 && !g_halo_init[device]) {
+    B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    g_halo_init[device] = 1;
+  }
+  HaloArgs p;
+  p.x = static_cast<const bf16*>(x->ptr);
+  p.w = static_cast<const bf16*>(wpk);
+  p.y = static_cast<bf16*>(y->ptr);
+  p.addend = addend ? static_cast<const bf16*>(addend->ptr) : nullptr;
+  p.bias = bias;
+  p.stats = stats;
+  p.xld = x->ld; p.yld = y->ld; p.ald = addend ? addend->ld : 0;
+  p.N = x->n; p.D = x->d; p.H = x->h; p.W = x->w;
+  p.Cin = x->c; p.Cout = y->c;
+  p.kd = dims == 3 ? 3 : 1;
+  p.tw = (p.W + HT_W - 1) / HT_W;
+  p.th = (p.H + HT_H - 1) / HT_H;
+  const int cols = p.N * p.th * p.tw;
+  const int sms = num_sms(device);
+  // split d so that the grid covers the chip (each extra chunk re-loads kd-1 halo slices)
+  int ndch = 1;
+  if (cols < sms) {
+    ndch = (sms + cols - 1) / cols;
+    if (ndch > p.D) ndch = p.D;
+  }
+  p.dchunk = (p.D + ndch - 1) / ndch;
+  p.ndchunks = (p.D + p.dchunk - 1) / p.dchunk;
+  p.nitems = cols * p.ndchunks;
+  const uint32_t slice = (uint32_t)(p.Cin / 8) * HP_H * HP_W * 16u;
+  const uint32_t wbytes = ((uint32_t)(p.kd * 9) * p.Cin * p.Cout * 2u + 127u) & ~127u;
+  const uint32_t tail = (2 * kHaloMaxSlices + 4) * 8 + 16 + 2 * p.Cout * 4 + 64;
+  int ns = (int)((maxsm - 256 - (int)wbytes - (int)tail) / (int)slice);
+  if (ns > kHaloMaxSlices) ns = kHaloMaxSlices;
+  B200_CHECK_ARG(ns >= p.kd + 1, "conv_halo: slices do not fit in shared memory");
+  p.nslices = ns;
+  int tc = 32;
+  while (tc < 2 * p.Cout) tc *= 2;
+  p.tmem_cols = tc;
+  static const int swap = [] {
+    const char* e = getenv("B200SEG_HALO_SWAP");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  p.swap_lbo_sbo = swap;
+  const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
+  int grid = sms < p.nitems ? sms : p.nitems;
+  conv_halo_kernel<<<grid, 288, smem_bytes, st>>>(p);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

@@ -89,7 +89,7 @@ class Engine:
     def conv_raw(self, kind: int, wname: str, bname: Optional[str], x: Tensor, y: Tensor,
                  stats: Optional[Tensor] = None) -> None:
         w = self.P[wname]
-        wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims)
+        wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims, vox=y.numel() // (y.shape[0] * y.shape[-1]))
         bias = self.P[bname] if bname is not None else None
         self.be.conv(kind, self.dims, x, wpk, bias, y, stats, None)
 
@@ -170,7 +170,7 @@ class Engine:
         be.unpack_wgrad(dwp, self._grad_view(L.wname), L.kind, self.dims)
         if not need_dx:
             return None
-        wd = be.pack_weight(w, L.kind, "dgrad", self.T, self.dims)
+        wd = be.pack_weight(w, L.kind, "dgrad", self.T, self.dims, vox=L.x.numel() // (L.x.shape[0] * L.x.shape[-1]))
         dkind = {K3: K3, K1: K1, DOWN: UP, UP: DOWN}[L.kind]
         if dx_out is None:
             dx_out = torch.empty(L.x.shape, dtype=self.T, device=dev)

@@ -34,7 +34,7 @@ class EmuBackend:
     name = "emu"
 
     # ------------------------------------------------------------------ weights
-    def pack_weight(self, w, kind, which, dtype, dims):
+    def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True, vox=None):
         """fwd : gather kinds -> [taps][Cin][Cout] ; UP -> [Cin][taps*Cout]
         dgrad: K3/K1 -> [taps(flipped)][Cout][Cin] ; DOWN -> [Cout][taps*Cin] ; UP -> [taps][Cout][Cin]"""
         a, b = w.shape[0], w.shape[1]

@@ -209,3 +209,44 @@ def test_tc_down_up_forward_dgrad_wgrad(be, kind, dims, n, sp, cin, cout):
     be.wgrad(DOWN, dims, fine.cuda().contiguous(), coarse.cuda().contiguous(), dw_c)
     torch.cuda.synchronize()
     assert rel(dw_c, dw_e) < 2e-5, rel(dw_c, dw_e)
+
+
+HALO_CASES = [
+    # dims, n, spatial, cin, cout
+    (3, 1, (6, 32, 16), 16, 16),
+    (3, 2, (5, 16, 24), 32, 32),
+    (3, 1, (4, 20, 12), 32, 16),          # ragged in h and w (tile overhang), UNet decoder 2C -> C
+    (3, 1, (3, 16, 8), 16, 32),
+    (2, 2, (1, 32, 32), 16, 16),
+    (2, 1, (1, 48, 40), 32, 32),
+    (3, 2, (40, 48, 48), 16, 16),         # more items than one CTA pass, d chunking
+]
+
+
+@pytest.mark.parametrize("dims,n,sp,cin,cout", HALO_CASES)
+@pytest.mark.parametrize("which", ["fwd", "dgrad"])
+def test_halo_conv_matches_emulation(be, dims, n, sp, cin, cout, which):
+    g = torch.Generator().manual_seed(13)
+    dt = torch.bfloat16
+    w = torch.randn((cout, cin) + (3,) * dims, generator=g) * (2.0 / (cin * 3 ** dims)) ** 0.5
+    ci, co = (cin, cout) if which == "fwd" else (cout, cin)
+    bias = torch.randn(co, generator=g) * 0.1
+    xbuf = torch.randn((n,) + sp + (ci + 16,), generator=g).to(dt)
+    x = xbuf[..., 8:8 + ci]
+    wp_c = be.pack_weight(w.cuda(), K3, which, dt, dims, vox=10 ** 9)
+    assert wp_c.code == 3, "expected the halo layout"
+    wp_e = EMU.pack_weight(w, K3, which, dt, dims)
+    for with_stats, with_addend in ((True, False), (False, True)):
+        y_e = torch.zeros((n,) + sp + (co,), dtype=dt)
+        ybuf = torch.zeros((n,) + sp + (co + 32,), dtype=dt, device="cuda")
+        y_c = ybuf[..., 16:16 + co]
+        st_e = torch.zeros(n, co, 2, dtype=torch.float64) if with_stats else None
+        st_c = st_e.clone().cuda() if with_stats else None
+        add = torch.randn((n,) + sp + (co,), generator=g).to(dt) if with_addend else None
+        EMU.conv(K3, dims, x, wp_e, bias, y_e, st_e, add)
+        be.conv(K3, dims, x.cuda(), wp_c, bias.cuda(), y_c, st_c, add.cuda() if with_addend else None)
+        torch.cuda.synchronize()
+        assert rel(y_c, y_e) < 6e-3, rel(y_c, y_e)
+        assert float(ybuf[..., :16].abs().max()) == 0 and float(ybuf[..., 16 + co:].abs().max()) == 0
+        if with_stats:
+            assert rel(st_c, st_e) < 1e-4
