@@ -15,7 +15,8 @@
 //   * loader warps move global -> registers -> smem with 128-bit accesses (this is where norm-on-load will be
 //     fused); MMA issue, TMEM double buffering and the epilogue (bias, GroupNorm statistics, residual
 //     addend, bf16 NDHWC stores) follow conv_tc.cu.
-// Warp roles (288 threads): warp 0 MMA issuer + TMEM allocator, warps 1-4 epilogue, warps 5-8 loaders.
+// Warp roles (416 threads): warp 0 MMA issuer + TMEM allocator, warps 1-4 epilogue, warps 5-12 loaders
+// (software-pipelined: the loads of slice i+1 are in flight while slice i is stored).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -25,6 +26,9 @@ namespace b200seg {
 constexpr int HT_W = 8, HT_H = 16;            // output tile (w, h); M = 128 rows = (hh, ww)
 constexpr int HP_W = HT_W + 2, HP_H = HT_H + 2;
 constexpr int kHaloMaxSlices = 8;
+constexpr int kLoaderWarps = 8;
+constexpr int kHaloThreads = 32 * (1 + 4 + kLoaderWarps);
+constexpr int kMaxPieces = (HP_H * HP_W * 4 + 32 * kLoaderWarps - 1) / (32 * kLoaderWarps);   // Cin <= 32
 
 struct HaloArgs {
   const bf16* x;
@@ -50,7 +54,7 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t 
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 
-__global__ void __launch_bounds__(288, 1) conv_halo_kernel(const HaloArgs p) {
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int CP = p.Cin / 8;                                  // 8-channel planes
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(288, 1) conv_halo_kernel(const HaloArgs p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslices; ++s) {
-      mbar_init(&sfull[s], 4);      // one arrive per loader warp
+      mbar_init(&sfull[s], kLoaderWarps);      // one arrive per loader warp
       mbar_init(&sempty[s], 1);     // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -118,6 +122,8 @@ __global__ void __launch_bounds__(288, 1) conv_halo_kernel(const HaloArgs p) {
     const uint32_t a_sbo = p.swap_lbo_sbo ? PLANE : HP_W * 16u;
     const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.Cout * 16u;
     const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)p.Cout * 16u : 128u;
+    const uint64_t a_hi = make_nosw_desc(0, a_lbo, a_sbo);
+    const uint64_t b_hi = make_nosw_desc(0, b_lbo, b_sbo);
     const uint32_t ring_u32 = smem_u32(s_ring);
     const uint32_t w_u32 = smem_u32(s_w);
     const int kchunks = p.Cin / 16;
@@ -147,9 +153,10 @@ __global__ void __launch_bounds__(288, 1) conv_halo_kernel(const HaloArgs p) {
               for (int kw_ = 0; kw_ < 3; ++kw_) {
                 const int tap = (kd_ * 3 + kh_) * 3 + kw_;
                 for (int kc = 0; kc < kchunks; ++kc) {
+                  // descriptors differ only in the 14-bit start-address field (16-byte units, smem < 256 KB)
                   const uint32_t a_addr = sbase + (uint32_t)(2 * kc) * PLANE + (uint32_t)(kh_ * HP_W + kw_) * 16u;
                   const uint32_t b_addr = w_u32 + (uint32_t)((tap * kchunks + kc) * 2 * p.Cout) * 16u;
-                  umma_bf16(tacc, make_nosw_desc(a_addr, a_lbo, a_sbo), make_nosw_desc(b_addr, b_lbo, b_sbo), idesc,
+                  umma_bf16(tacc, a_hi | (uint64_t)(a_addr >> 4), b_hi | (uint64_t)(b_addr >> 4), idesc,
                             first ? 0u : 1u);
                   first = 0;
                 }
@@ -166,36 +173,70 @@ __global__ void __launch_bounds__(288, 1) conv_halo_kernel(const HaloArgs p) {
       gs += (uint32_t)nsl;
     }
   } else if (warp >= 5) {
-    // ===================================================== loaders (128 threads)
+    // ===================================================== loaders (8 warps, software pipelined)
+    constexpr int LT = 32 * kLoaderWarps;
     const int lt = threadIdx.x - 160;
     const int pieces = HP_H * HP_W * CP;
-    uint32_t gs = 0;
-    for (int item = item_begin; item < item_end; ++item) {
-      int n, h0, w0, d0, nd;
-      decode(item, n, h0, w0, d0, nd);
-      const int nsl = nd + p.kd - 1;
-      for (int i = 0; i < nsl; ++i) {
-        const uint32_t sl = gs + i;
-        const uint32_t slot = sl % p.nslices;
-        mbar_wait(&sempty[slot], ((sl / p.nslices) & 1u) ^ 1u);
-        const int d = d0 - pd + i;
-        const bool dok = (unsigned)d < (unsigned)p.D;
-        uint8_t* dst = s_ring + (size_t)slot * SLICE;
-        const bf16* src = p.x + (((long long)n * p.D + (dok ? d : 0)) * p.H) * p.W * p.xld;
-        for (int q = lt; q < pieces; q += 128) {
-          const int v = q / CP, plane = q - v * CP;
-          const int hh = v / HP_W, ww = v - hh * HP_W;
-          const int h = h0 - 1 + hh, w = w0 - 1 + ww;
-          uint4 val = make_uint4(0u, 0u, 0u, 0u);
-          if (dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
-            val = *reinterpret_cast<const uint4*>(src + ((long long)h * p.W + w) * p.xld + plane * 8);
-          *reinterpret_cast<uint4*>(dst + (size_t)plane * PLANE + (size_t)v * 16) = val;
-        }
-        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sfull[slot]);
+    // this thread's pieces: q = lt + j*LT  ->  (voxel v, plane) -> smem offset and (hh, ww)
+    int poff[kMaxPieces], phh[kMaxPieces], pww[kMaxPieces];
+    bool pval[kMaxPieces];
+#pragma unroll
+    for (int j = 0; j < kMaxPieces; ++j) {
+      const int q = lt + j * LT;
+      pval[j] = q < pieces;
+      const int qq = pval[j] ? q : 0;
+      const int v = qq / CP, plane = qq - v * CP;
+      phh[j] = v / HP_W;
+      pww[j] = v - phh[j] * HP_W;
+      poff[j] = plane * (int)PLANE + v * 16;
+      // global element offset of the plane is added per slice below
+      pww[j] |= plane << 16;
+    }
+    // iterator over (item, slice)
+    int it_item = item_begin, it_i = 0, it_nsl = 0, n = 0, h0 = 0, w0 = 0, d0 = 0, nd = 0;
+    if (it_item < item_end) {
+      decode(it_item, n, h0, w0, d0, nd);
+      it_nsl = nd + p.kd - 1;
+    }
+    uint4 regs[kMaxPieces];
+    auto issue_loads = [&]() {
+      const int d = d0 - pd + it_i;
+      const bool dok = (unsigned)d < (unsigned)p.D;
+      const bf16* src = p.x + (((long long)n * p.D + (dok ? d : 0)) * p.H) * p.W * p.xld;
+#pragma unroll
+      for (int j = 0; j < kMaxPieces; ++j) {
+        const int plane = pww[j] >> 16, ww = pww[j] & 0xffff;
+        const int h = h0 - 1 + phh[j], w = w0 - 1 + ww;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (pval[j] && dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
+          val = *reinterpret_cast<const uint4*>(src + ((long long)h * p.W + w) * p.xld + plane * 8);
+        regs[j] = val;
       }
-      gs += (uint32_t)nsl;
+    };
+    uint32_t sl = 0;
+    if (it_item < item_end) issue_loads();
+    while (it_item < item_end) {
+      const uint32_t slot = sl % p.nslices;
+      mbar_wait(&sempty[slot], ((sl / p.nslices) & 1u) ^ 1u);
+      uint8_t* dst = s_ring + (size_t)slot * SLICE;
+#pragma unroll
+      for (int j = 0; j < kMaxPieces; ++j)
+        if (pval[j]) *reinterpret_cast<uint4*>(dst + poff[j]) = regs[j];
+      // advance and put the next slice's loads in flight before signalling this one
+      ++it_i;
+      if (it_i == it_nsl) {
+        ++it_item;
+        it_i = 0;
+        if (it_item < item_end) {
+          decode(it_item, n, h0, w0, d0, nd);
+          it_nsl = nd + p.kd - 1;
+        }
+      }
+      fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[slot]);
+      if (it_item < item_end) issue_loads();
+      ++sl;
     }
   } else {
     // ===================================================== epilogue warps 1..4
@@ -346,8 +387,9 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   // split d so that the grid covers the chip (each extra chunk re-loads kd-1 halo slices)
   int ndch = 1;
   if (cols < sms) {
-    ndch = (sms + cols - 1) / cols;
+    ndch = sms / cols;                 // items <= #SM: one item per CTA, no second wave
     if (ndch > p.D) ndch = p.D;
+    if (ndch < 1) ndch = 1;
   }
   p.dchunk = (p.D + ndch - 1) / ndch;
   p.ndchunks = (p.D + p.dchunk - 1) / p.dchunk;
@@ -369,7 +411,7 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.swap_lbo_sbo = swap;
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = sms < p.nitems ? sms : p.nitems;
-  conv_halo_kernel<<<grid, 288, smem_bytes, st>>>(p);
+  conv_halo_kernel<<<grid, kHaloThreads, smem_bytes, st>>>(p);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

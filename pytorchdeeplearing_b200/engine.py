@@ -55,6 +55,26 @@ def _taps(kind: int, dims: int) -> int:
     return 8 if dims == 3 else 4
 
 
+class _ZeroArena:
+    """One zero-filled allocation per pass, handed out as views: replaces ~100 tiny fill launches per step
+    (GroupNorm statistics, backward sums, split-K weight-gradient accumulators) by one memset each."""
+
+    def __init__(self, dtype: torch.dtype, numel: int, device):
+        self.buf = torch.zeros(max(1, numel), dtype=dtype, device=device)
+        self.off = 0
+
+    def take(self, shape) -> Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        n_al = (n + 15) // 16 * 16                      # keep every view 128-byte aligned
+        if self.off + n_al > self.buf.numel():
+            return torch.zeros(shape, dtype=self.buf.dtype, device=self.buf.device)
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return v
+
+
 class Engine:
     """Executes the layer program on ``backend``.  ``P`` maps reference state_dict names to
     fp32 parameter tensors (App. A layout)."""
@@ -70,13 +90,28 @@ class Engine:
         self.grads: Dict[str, Tensor] = {}
         self.saved: Dict[str, object] = {}
         self.need_grad = True
+        self._z64 = None
+        self._z32 = None
 
     # ---------------------------------------------------------------- allocation helpers
     def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
         return torch.empty((like.shape[0],) + tuple(sp) + (c,), dtype=dtype or self.T, device=like.device)
 
     def zeros(self, shape, dtype, device) -> Tensor:
+        arena = self._z64 if dtype == torch.float64 else (self._z32 if dtype == torch.float32 else None)
+        if arena is not None and arena.buf.device == device:
+            return arena.take(tuple(shape))
         return torch.zeros(shape, dtype=dtype, device=device)
+
+    def _begin_pass(self, n: int, device, backward: bool) -> None:
+        gn_ch = sum(p.numel() for k, p in self.P.items() if p.dim() == 1 and k.endswith(".weight"))
+        per = 3 if backward else 2
+        self._z64 = _ZeroArena(torch.float64, n * gn_ch * per * 2 + 64 * 40, device)
+        if backward:
+            wel = sum(p.numel() for p in self.P.values() if p.dim() > 1)
+            self._z32 = _ZeroArena(torch.float32, wel + 16 * 64, device)
+        else:
+            self._z32 = None
 
     def _next_mask(self) -> Optional[Tensor]:
         if self.masks is None:
@@ -197,6 +232,7 @@ class Engine:
         self.P, self.masks, self._mi, self.layers, self.need_grad = P, masks, 0, [], need_grad
         sv = self.saved = {}
         n, cin = x.shape[0], x.shape[1]
+        self._begin_pass(n, x.device, backward=False)
         sp0 = tuple(x.shape[2:])
         xin = x.permute(0, 2, 3, 4, 1)
         if cin != 1:
@@ -265,6 +301,7 @@ class Engine:
         channels-last).  Returns the flat fp32 bucket; ``self.grads`` holds the views."""
         sv = self.saved
         flat = self.alloc_grads(g_logits.device)
+        self._begin_pass(g_logits.shape[0], g_logits.device, backward=True)
         g = self.head_backward(sv["head"], g_logits)
         gskip: List[Optional[Tensor]] = [None] * 4
         for i, name in zip((0, 1, 2, 3), ["up_tr32", "up_tr64", "up_tr128", "up_tr256"]):
@@ -297,6 +334,7 @@ class Engine:
         sv = self.saved = {}
         dims = self.dims
         n, cin = x.shape[0], x.shape[1]
+        self._begin_pass(n, x.device, backward=False)
         if dims == 3:
             sp0 = tuple(x.shape[2:])
             xin = x.permute(0, 2, 3, 4, 1)
@@ -346,6 +384,7 @@ class Engine:
     def unet_backward(self, g_logits: Tensor) -> Tensor:
         sv = self.saved
         flat = self.alloc_grads(g_logits.device)
+        self._begin_pass(g_logits.shape[0], g_logits.device, backward=True)
         g = self.head_backward(sv["head"], g_logits)
         genc: List[Optional[Tensor]] = [None] * 4
         for i in (0, 1, 2, 3):
