@@ -47,6 +47,7 @@ struct HaloArgs {
   int nslices;            // ring size
   int tmem_cols;
   int swap_lbo_sbo;       // debug: swap the roles of the two descriptor strides
+  int cp_async;           // 1: loaders use cp.async (zfill) + mbarrier completion; 0: register-staged copies
 };
 
 __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
   uint64_t* tfull = sempty + kHaloMaxSlices;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [2][Cout]
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslices; ++s) {
-      mbar_init(&sfull[s], kLoaderWarps);      // one arrive per loader warp
+      // register loader: one arrive per loader warp; cp.async loader: one (deferred) arrive per loader thread
+      mbar_init(&sfull[s], p.cp_async ? 32 * kLoaderWarps : kLoaderWarps);
       mbar_init(&sempty[s], 1);     // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
   // resident weights: straight 16-byte copy of the pre-packed smem image
   for (uint32_t i = threadIdx.x * 16u; i < W_BYTES; i += blockDim.x * 16u)
     *reinterpret_cast<uint4*>(s_w + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + i);
-  for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
         }
         const uint32_t as = go & 1u;
         mbar_wait(&tempty[as], ((go >> 1) & 1u) ^ 1u);
+        // slices written by cp.async (generic proxy) must be ordered before the tensor core's async-proxy reads
+        fence_proxy_async();
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout;
@@ -214,6 +218,40 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
       }
     };
     uint32_t sl = 0;
+    if (p.cp_async) {
+      // fully asynchronous: as many slices in flight as the ring has free slots
+      while (it_item < item_end) {
+        const uint32_t slot = sl % p.nslices;
+        mbar_wait(&sempty[slot], ((sl / p.nslices) & 1u) ^ 1u);
+        const uint32_t dst = smem_u32(s_ring + (size_t)slot * SLICE);
+        const int d = d0 - pd + it_i;
+        const bool dok = (unsigned)d < (unsigned)p.D;
+        const bf16* src = p.x + (((long long)n * p.D + (dok ? d : 0)) * p.H) * p.W * p.xld;
+#pragma unroll
+        for (int j = 0; j < kMaxPieces; ++j) {
+          if (!pval[j]) continue;
+          const int plane = pww[j] >> 16, ww = pww[j] & 0xffff;
+          const int h = h0 - 1 + phh[j], w = w0 - 1 + ww;
+          const bool ok = dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+          const bf16* g = ok ? src + ((long long)h * p.W + w) * p.xld + plane * 8 : p.x;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)poff[j]), "l"(g),
+                       "r"(ok ? 16 : 0)
+                       : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sfull[slot])) : "memory");
+        ++it_i;
+        if (it_i == it_nsl) {
+          ++it_item;
+          it_i = 0;
+          if (it_item < item_end) {
+            decode(it_item, n, h0, w0, d0, nd);
+            it_nsl = nd + p.kd - 1;
+          }
+        }
+        ++sl;
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
     if (it_item < item_end) issue_loads();
     while (it_item < item_end) {
       const uint32_t slot = sl % p.nslices;
@@ -238,6 +276,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
       if (it_item < item_end) issue_loads();
       ++sl;
     }
+    }
   } else {
     // ===================================================== epilogue warps 1..4
     const int q = warp & 3;
@@ -251,8 +290,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
       if (p.stats != nullptr && n >= 0) {
         for (int i = etid; i < 2 * p.Cout; i += 128) {
           const int which = i / p.Cout, c = i - which * p.Cout;
-          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, (double)s_stat[i]);
-          s_stat[i] = 0.f;
+          double t = 0.0;
+#pragma unroll
+          for (int wq = 0; wq < 4; ++wq) {
+            t += (double)s_stat[wq * 2 * p.Cout + i];
+            s_stat[wq * 2 * p.Cout + i] = 0.f;
+          }
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -303,8 +347,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
             qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
             if ((lane & 1) == 0) {
               const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              atomicAdd(&s_stat[c0 + col], s[0]);
-              atomicAdd(&s_stat[p.Cout + c0 + col], qq[0]);
+              // this lane is the only writer of its column in this warp's private row: no atomics, fixed order
+              float* sw_ = s_stat + q * 2 * p.Cout;
+              sw_[c0 + col] += s[0];
+              sw_[p.Cout + c0 + col] += qq[0];
             }
           }
           if (valid) {
@@ -396,7 +442,7 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.nitems = cols * p.ndchunks;
   const uint32_t slice = (uint32_t)(p.Cin / 8) * HP_H * HP_W * 16u;
   const uint32_t wbytes = ((uint32_t)(p.kd * 9) * p.Cin * p.Cout * 2u + 127u) & ~127u;
-  const uint32_t tail = (2 * kHaloMaxSlices + 4) * 8 + 16 + 2 * p.Cout * 4 + 64;
+  const uint32_t tail = (2 * kHaloMaxSlices + 4) * 8 + 16 + 8 * p.Cout * 4 + 64;
   int ns = (int)((maxsm - 256 - (int)wbytes - (int)tail) / (int)slice);
   if (ns > kHaloMaxSlices) ns = kHaloMaxSlices;
   B200_CHECK_ARG(ns >= p.kd + 1, "conv_halo: slices do not fit in shared memory");
@@ -409,6 +455,11 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     return (e && e[0] == '1') ? 1 : 0;
   }();
   p.swap_lbo_sbo = swap;
+  static const int cpa = [] {
+    const char* e = getenv("B200SEG_HALO_LOADER");
+    return (e && e[0] == 'r') ? 0 : 1;          // "regs" selects the register-staged loader
+  }();
+  p.cp_async = cpa;
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = sms < p.nitems ? sms : p.nitems;
   conv_halo_kernel<<<grid, kHaloThreads, smem_bytes, st>>>(p);

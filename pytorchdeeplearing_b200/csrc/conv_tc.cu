@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);     // [2][Cout]
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);     // [4 epilogue warps][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,8 +189,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       if (p.stats != nullptr && n >= 0) {
         for (int i = etid; i < 2 * p.Cout; i += 128) {
           const int which = i / p.Cout, c = i - which * p.Cout;
-          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, (double)s_stat[i]);
-          s_stat[i] = 0.f;
+          double t = 0.0;
+#pragma unroll
+          for (int wq = 0; wq < 4; ++wq) {
+            t += (double)s_stat[wq * 2 * p.Cout + i];
+            s_stat[wq * 2 * p.Cout + i] = 0.f;
+          }
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -258,8 +263,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           if ((lane & 1) == 0) {
             // column owned by this lane: bit k of the index is bit (4-k) of the lane for k = 0..3
             const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            atomicAdd(&s_stat[c0 + col], s[0]);
-            atomicAdd(&s_stat[p.Cout + c0 + col], qq[0]);
+            // this lane is the only writer of its column in this warp's private row: no atomics, fixed order
+            float* sw_ = s_stat + q * 2 * p.Cout;
+            sw_[c0 + col] += s[0];
+            sw_[p.Cout + c0 + col] += qq[0];
           }
         }
         if (valid) {
@@ -396,7 +403,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const uint32_t a_bytes = 128u * swz;
   const uint32_t b_bytes = (((uint32_t)p.Ntile * swz) + 1023u) & ~1023u;
   const uint32_t stage = a_bytes + b_bytes;
-  const uint32_t tail = (2 * kMaxStages + 4) * 8 + 16 + 2 * p.Cout * 4;
+  const uint32_t tail = (2 * kMaxStages + 4) * 8 + 16 + 8 * p.Cout * 4;
   const int maxsm = g_smem_optin[device] > 0 ? g_smem_optin[device] : 227 * 1024;
   int nst = (int)((maxsm - 1024 - (int)tail - 256) / (int)stage);
   if (nst > kMaxStages) nst = kMaxStages;

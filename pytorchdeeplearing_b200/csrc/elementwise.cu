@@ -129,23 +129,45 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
       B2[j] = 0.f;
     }
   }
-  for (; gi < total; gi += stride) {
-    long long vox = (long long)n * V + gi / G;
-    float a[VEC], o[VEC];
-    Vec<T, VEC>::load(y1 + vox * ld1 + c0, a);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) o[j] = fmaxf(fmaf(a[j], A1[j], B1[j]), 0.f);
+  for (; gi < total; gi += 2 * stride) {
+    // two voxel groups per trip, loads first
+    const long long gi2 = gi + stride;
+    const bool two = gi2 < total;
+    const long long vox0 = (long long)n * V + gi / G;
+    const long long vox1 = (long long)n * V + (two ? gi2 : gi) / G;
+    float a0[VEC], a1[VEC], b0[VEC], b1[VEC], r0[VEC], r1[VEC];
+    Vec<T, VEC>::load(y1 + vox0 * ld1 + c0, a0);
+    Vec<T, VEC>::load(y1 + vox1 * ld1 + c0, a1);
     if (y2 != nullptr) {
-      Vec<T, VEC>::load(y2 + vox * ld2 + c0, a);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) o[j] += fmaxf(fmaf(a[j], A2[j], B2[j]), 0.f);
+      Vec<T, VEC>::load(y2 + vox0 * ld2 + c0, b0);
+      Vec<T, VEC>::load(y2 + vox1 * ld2 + c0, b1);
     }
     if (res != nullptr) {
-      Vec<T, VEC>::load(res + vox * ldr + c0, a);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) o[j] += a[j];
+      Vec<T, VEC>::load(res + vox0 * ldr + c0, r0);
+      Vec<T, VEC>::load(res + vox1 * ldr + c0, r1);
     }
-    Vec<T, VEC>::store(out + vox * ldo + c0, o);
+    float o0[VEC], o1[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      o0[j] = fmaxf(fmaf(a0[j], A1[j], B1[j]), 0.f);
+      o1[j] = fmaxf(fmaf(a1[j], A1[j], B1[j]), 0.f);
+    }
+    if (y2 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        o0[j] += fmaxf(fmaf(b0[j], A2[j], B2[j]), 0.f);
+        o1[j] += fmaxf(fmaf(b1[j], A2[j], B2[j]), 0.f);
+      }
+    }
+    if (res != nullptr) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        o0[j] += r0[j];
+        o1[j] += r1[j];
+      }
+    }
+    Vec<T, VEC>::store(out + vox0 * ldo + c0, o0);
+    if (two) Vec<T, VEC>::store(out + vox1 * ldo + c0, o1);
   }
 }
 
@@ -172,17 +194,38 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
     B[j] = p[1];
     s1[j] = s2[j] = s3[j] = 0.0;
   }
-  for (; gi < total; gi += stride) {
-    long long vox = (long long)n * V + gi / G;
-    float yv[VEC], gv[VEC];
-    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
-    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
+  // 4 voxel groups per trip: all 8 loads are issued before the first use (memory-level parallelism), their
+  // contributions are added in fp32 and flushed into the fp64 accumulators once per trip
+  for (; gi < total; gi += 4 * stride) {
+    float yv[4][VEC], gv[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long g2 = gi + u * stride;
+      if (g2 < total) {
+        const long long vox = (long long)n * V + g2 / G;
+        Vec<T, VEC>::load(y + vox * ldy + c0, yv[u]);
+        Vec<T, VEC>::load(g + vox * ldg + c0, gv[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          yv[u][j] = 0.f;
+          gv[u][j] = 0.f;
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] : 0.f;
-      s1[j] += (double)d;
-      s2[j] += (double)d * (double)yv[j];
-      s3[j] += (double)yv[j];
+      float f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d = fmaf(yv[u][j], A[j], B[j]) > 0.f ? gv[u][j] : 0.f;
+        f1 += d;
+        f2 = fmaf(d, yv[u][j], f2);
+        f3 += yv[u][j];
+      }
+      s1[j] += (double)f1;
+      s2[j] += (double)f2;
+      s3[j] += (double)f3;
     }
   }
   // lanes l and l ^ off share the channel group when off is a multiple of G (G a power of two <= 16)
@@ -277,17 +320,25 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
     Q[j] = q[1];
     R[j] = q[2];
   }
-  for (; gi < total; gi += stride) {
-    long long vox = (long long)n * V + gi / G;
-    float yv[VEC], gv[VEC], o[VEC];
-    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
-    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
+  for (; gi < total; gi += 2 * stride) {
+    const long long gi2 = gi + stride;
+    const bool two = gi2 < total;
+    const long long vox0 = (long long)n * V + gi / G;
+    const long long vox1 = (long long)n * V + (two ? gi2 : gi) / G;
+    float y0[VEC], y1v[VEC], g0[VEC], g1[VEC], o0[VEC], o1[VEC];
+    Vec<T, VEC>::load(y + vox0 * ldy + c0, y0);
+    Vec<T, VEC>::load(y + vox1 * ldy + c0, y1v);
+    Vec<T, VEC>::load(g + vox0 * ldg + c0, g0);
+    Vec<T, VEC>::load(g + vox1 * ldg + c0, g1);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] * P[j] : 0.f;
-      o[j] = d + fmaf(yv[j], Q[j], R[j]);
+      const float d0 = fmaf(y0[j], A[j], B[j]) > 0.f ? g0[j] * P[j] : 0.f;
+      const float d1 = fmaf(y1v[j], A[j], B[j]) > 0.f ? g1[j] * P[j] : 0.f;
+      o0[j] = d0 + fmaf(y0[j], Q[j], R[j]);
+      o1[j] = d1 + fmaf(y1v[j], Q[j], R[j]);
     }
-    Vec<T, VEC>::store(dy + vox * ldd + c0, o);
+    Vec<T, VEC>::store(dy + vox0 * ldd + c0, o0);
+    if (two) Vec<T, VEC>::store(dy + vox1 * ldd + c0, o1);
   }
 }
 
