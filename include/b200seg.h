@@ -74,6 +74,22 @@ int b200seg_pack_weight(const float* w, void* out, int out_dtype, int T, int K, 
 int b200seg_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, int64_t st, int64_t sk, int64_t sn,
                          int device, b200seg_stream stream);
 
+/* Multi-tensor forms of the two calls above: ONE launch for every conv operand of a network.  `table` is a DEVICE
+ * array of `count` descriptors; descriptor i owns thread blocks [block_start, block_start + nblocks) and
+ * total_blocks = sum of nblocks.  pack: dst[t][k][n2][n1] (out_dtype) = src[tmap(t)*st + k*sk + n2*sn2 + n1*sn1];
+ * unpack: dst[t*st + k*sk + n*sn2] = src[(t*K + k)*N2 + n] (fp32, N1 ignored). */
+typedef struct b200seg_pack_desc {
+  const float* src;
+  void* dst;
+  int64_t st, sk, sn2, sn1;
+  int32_t out_dtype, T, K, N2, N1, flip;
+  int32_t block_start, nblocks;
+} b200seg_pack_desc;
+int b200seg_pack_weights_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,
+                               b200seg_stream stream);
+int b200seg_unpack_wgrads_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,
+                                b200seg_stream stream);
+
 /* ---- convolution family (replaces F.conv3d / F.conv_transpose3d / F.conv2d, call sites above;
  * the data-gradient half of aten::convolution_backward runs through the same entry with
  * dgrad-packed weights).

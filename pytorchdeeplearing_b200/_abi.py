@@ -25,6 +25,12 @@ class TensorDesc(C.Structure):
                 ("c", C.c_int32), ("ld", C.c_int64), ("dtype", C.c_int32)]
 
 
+class PackDesc(C.Structure):   # include/b200seg.h: struct b200seg_pack_desc
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("st", C.c_int64), ("sk", C.c_int64), ("sn2", C.c_int64),
+                ("sn1", C.c_int64), ("out_dtype", C.c_int32), ("T", C.c_int32), ("K", C.c_int32), ("N2", C.c_int32),
+                ("N1", C.c_int32), ("flip", C.c_int32), ("block_start", C.c_int32), ("nblocks", C.c_int32)]
+
+
 _PT = C.POINTER(TensorDesc)
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -34,6 +40,8 @@ _SIGNATURES = {
     "b200seg_init": ([_i], C.c_int),
     "b200seg_pack_weight": ([_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp], C.c_int),
     "b200seg_unpack_wgrad": ([_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp], C.c_int),
+    "b200seg_pack_weights_multi": ([_vp, _i, _i, _i, _vp], C.c_int),
+    "b200seg_unpack_wgrads_multi": ([_vp, _i, _i, _i, _vp], C.c_int),
     "b200seg_conv": ([_i, _i, _PT, _vp, _i, _vp, _PT, _vp, _PT, _i, _vp], C.c_int),
     "b200seg_conv_tc_eligible": ([_i, _i, _i], C.c_int),
     "b200seg_conv_halo_eligible": ([_i, _i, _i], C.c_int),
@@ -141,6 +149,7 @@ class CudaBackend:
         self.use_tc = os.environ.get("B200SEG_DISABLE_TC", "0") != "1"
         self.use_halo = os.environ.get("B200SEG_DISABLE_HALO", "0") != "1"
         self.halo_min_vox = int(os.environ.get("B200SEG_HALO_MIN_VOX", str(128 * 128)))
+        self._pinned_forever, self._pinned_ring, self._keep_tables = [], [], []
         self.launch_count = 0      # kernels launched through the C ABI (one per successful entry-point call)
 
     # ------------------------------------------------------------------ plumbing
@@ -158,29 +167,19 @@ class CudaBackend:
         self.launch_count += 1
 
     # ------------------------------------------------------------------ weights
-    def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True, vox=None):
-        """``vox``: voxels per sample of the layer's output (lets the backend pick the halo-staged kernel for the
-        full-resolution 16/32-channel layers)."""
+    def _pack_plan(self, w, kind, which, dtype, dims, allow_tc=True, vox=None):
+        """-> (out_shape, layout code, (T, K, N2, N1, st, sk, sn2, sn1, flip)) for one conv operand."""
         a, b = w.shape[0], w.shape[1]
         t = w.numel() // (a * b)
-        dev, st = self._ds(w)
         od = F32 if dtype == torch.float32 else BF16
-        code = od
-        tc = False
         if (allow_tc and self.use_tc and self.use_halo and dtype == torch.bfloat16 and kind == K3
                 and vox is not None and vox >= self.halo_min_vox):
             cin, cout = (b, a) if which == "fwd" else (a, b)
             if self.lib.b200seg_conv_halo_eligible(kind, cin, cout):
                 if which == "fwd":      # [t][ci/8][co][ci%8]
-                    out = torch.empty((t, b // 8, a, 8), dtype=dtype, device=w.device)
-                    args = (t, b // 8, a, 8, 1, 8 * t, b * t, t, 0)
-                else:                   # [T-1-t][co/8][ci][co%8]
-                    out = torch.empty((t, a // 8, b, 8), dtype=dtype, device=w.device)
-                    args = (t, a // 8, b, 8, 1, 8 * b * t, t, b * t, 1)
-                T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
-                self._check(self.lib.b200seg_pack_weight(w.data_ptr(), out.data_ptr(), od, T, K, N2, N1, s_t, s_k,
-                                                         s_n2, s_n1, flip, dev, st))
-                return PackedWeight(out, BF16_HALO, w, kind, which, dims)
+                    return (t, b // 8, a, 8), BF16_HALO, (t, b // 8, a, 8, 1, 8 * t, b * t, t, 0)
+                return (t, a // 8, b, 8), BF16_HALO, (t, a // 8, b, 8, 1, 8 * b * t, t, b * t, 1)   # [T-1-t][co/8][ci][co%8]
+        tc = False
         if allow_tc and self.use_tc and dtype == torch.bfloat16:
             # (kind, Cin, Cout) of the op that will consume the packed operand
             if which == "fwd":
@@ -190,38 +189,86 @@ class CudaBackend:
             tc = bool(self.lib.b200seg_conv_tc_eligible(*op))
         if tc:
             # K-major rows for the tcgen05 path: [tap][N][K]
-            code = BF16_TC
             gather_like = (which == "fwd" and kind != UP) or (which == "dgrad" and kind == UP)
             if which == "dgrad" and kind in (K3, K1):      # [T-1-t][ci][co]
-                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
-                args = (t, b, 1, a, 1, t, 0, b * t, 1)
-            elif gather_like:                               # W (A,B,t) -> [t][A][B]
-                out = torch.empty((t, a, b), dtype=dtype, device=w.device)
-                args = (t, a, 1, b, 1, b * t, 0, t, 0)
-            else:                                           # W (A,B,t) -> [t][B][A]  (UP fwd, DOWN dgrad)
-                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
-                args = (t, b, 1, a, 1, t, 0, b * t, 0)
-        elif which == "fwd":
+                return (t, b, a), BF16_TC, (t, b, 1, a, 1, t, 0, b * t, 1)
+            if gather_like:                                 # W (A,B,t) -> [t][A][B]
+                return (t, a, b), BF16_TC, (t, a, 1, b, 1, b * t, 0, t, 0)
+            return (t, b, a), BF16_TC, (t, b, 1, a, 1, t, 0, b * t, 0)   # [t][B][A]  (UP fwd, DOWN dgrad)
+        if which == "fwd":
             if kind == UP:      # W (Ci,Co,t) -> [ci][t*Co + co]
-                out = torch.empty((a, t * b), dtype=dtype, device=w.device)
-                args = (1, a, t, b, 0, b * t, 1, t, 0)
-            else:               # W (Co,Ci,t) -> [t][ci][co]
-                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
-                args = (t, b, 1, a, 1, t, 0, b * t, 0)
-        else:
-            if kind in (K3, K1):   # [T-1-t][co][ci]
-                out = torch.empty((t, a, b), dtype=dtype, device=w.device)
-                args = (t, a, 1, b, 1, b * t, 0, t, 1)
-            elif kind == DOWN:     # W (Co,Ci,t) -> [co][t*Ci + ci]
-                out = torch.empty((a, t * b), dtype=dtype, device=w.device)
-                args = (1, a, t, b, 0, b * t, 1, t, 0)
-            else:                  # UP: W (Ci,Co,t) -> [t][co][ci]
-                out = torch.empty((t, b, a), dtype=dtype, device=w.device)
-                args = (t, b, 1, a, 1, t, 0, b * t, 0)
+                return (a, t * b), od, (1, a, t, b, 0, b * t, 1, t, 0)
+            return (t, b, a), od, (t, b, 1, a, 1, t, 0, b * t, 0)       # W (Co,Ci,t) -> [t][ci][co]
+        if kind in (K3, K1):   # [T-1-t][co][ci]
+            return (t, a, b), od, (t, a, 1, b, 1, b * t, 0, t, 1)
+        if kind == DOWN:       # W (Co,Ci,t) -> [co][t*Ci + ci]
+            return (a, t * b), od, (1, a, t, b, 0, b * t, 1, t, 0)
+        return (t, b, a), od, (t, b, 1, a, 1, t, 0, b * t, 0)           # UP: W (Ci,Co,t) -> [t][co][ci]
+
+    def pack_weight(self, w, kind, which, dtype, dims, allow_tc=True, vox=None):
+        """``vox``: voxels per sample of the layer's output (lets the backend pick the halo-staged kernel for the
+        full-resolution 16/32-channel layers)."""
+        dev, st = self._ds(w)
+        shape, code, args = self._pack_plan(w, kind, which, dtype, dims, allow_tc, vox)
+        out = torch.empty(shape, dtype=dtype, device=w.device)
+        od = F32 if dtype == torch.float32 else BF16
         T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
         self._check(self.lib.b200seg_pack_weight(w.data_ptr(), out.data_ptr(), od, T, K, N2, N1, s_t, s_k, s_n2, s_n1,
                                                  flip, dev, st))
         return PackedWeight(out, code, w, kind, which, dims)
+
+    def _table_to_device(self, descs, device):
+        """ctypes descriptor array -> pinned host tensor -> device tensor (async copy on the current stream)."""
+        arr = (PackDesc * len(descs))(*descs)
+        raw = bytes(arr)
+        host = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
+        host.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        devt = host.to(device, non_blocking=True)
+        # the pinned buffer must outlive the (possibly graph-captured) copy
+        if torch.cuda.is_current_stream_capturing():
+            self._pinned_forever.append(host)
+        else:
+            self._pinned_ring.append(host)
+            if len(self._pinned_ring) > 32:
+                self._pinned_ring.pop(0)
+        return devt
+
+    def pack_many(self, reqs):
+        """reqs: [(w, kind, which, dtype, dims, vox)] -> [PackedWeight]: ONE launch for all operands."""
+        if not reqs:
+            return []
+        dev, st = self._ds(reqs[0][0])
+        descs, outs, blocks = [], [], 0
+        for (w, kind, which, dtype, dims, vox) in reqs:
+            shape, code, args = self._pack_plan(w, kind, which, dtype, dims, True, vox)
+            out = torch.empty(shape, dtype=dtype, device=w.device)
+            T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
+            nb = max(1, min(64, (out.numel() + 1023) // 1024))
+            descs.append(PackDesc(w.data_ptr(), out.data_ptr(), s_t, s_k, s_n2, s_n1,
+                                  F32 if dtype == torch.float32 else BF16, T, K, N2, N1, flip, blocks, nb))
+            blocks += nb
+            outs.append(PackedWeight(out, code, w, kind, which, dims))
+        table = self._table_to_device(descs, reqs[0][0].device)
+        self._check(self.lib.b200seg_pack_weights_multi(table.data_ptr(), len(descs), blocks, dev, st))
+        self._keep_tables.append(table)
+        if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
+            self._keep_tables.pop(0)
+        return outs
+
+    def unpack_many(self, items):
+        """items: [(dwp [t][k][n], grad view)] -> parameter-layout gradients, ONE launch."""
+        if not items:
+            return
+        dev, st = self._ds(items[0][0])
+        descs, blocks = [], 0
+        for dwp, grad in items:
+            t, k, n = dwp.shape
+            nb = max(1, min(64, (dwp.numel() + 1023) // 1024))
+            descs.append(PackDesc(dwp.data_ptr(), grad.data_ptr(), 1, t, k * t, 0, F32, t, k, n, 1, 0, blocks, nb))
+            blocks += nb
+        table = self._table_to_device(descs, items[0][0].device)
+        self._check(self.lib.b200seg_unpack_wgrads_multi(table.data_ptr(), len(descs), blocks, dev, st))
+        self._keep_tables.append(table)
 
     def unpack_wgrad(self, dwp, grad, kind, dims):
         t, k, n = dwp.shape

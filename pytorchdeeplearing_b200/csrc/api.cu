@@ -50,6 +50,7 @@ int ew_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N
                    long long sk, long long sn2, long long sn1, int flip, cudaStream_t s);
 int ew_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, long long st, long long sk, long long sn,
                     cudaStream_t s);
+int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack, cudaStream_t s);
 int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
                    int groups, long long vox, float eps, float* coef, float* mr, cudaStream_t s);
 int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_tensor* y2, const float* c2,
@@ -110,6 +111,20 @@ int b200seg_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, int
   B200_CHECK_ARG(dwp && grad && T > 0 && K > 0 && N > 0, "b200seg_unpack_wgrad: bad argument");
   B200_DEVICE(device);
   return ew_unpack_wgrad(dwp, grad, T, K, N, st, sk, sn, ST(stream));
+}
+
+int b200seg_pack_weights_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,
+                               b200seg_stream stream) {
+  B200_CHECK_ARG(table != nullptr && count >= 0 && total_blocks >= 0, "b200seg_pack_weights_multi: bad argument");
+  B200_DEVICE(device);
+  return ew_pack_multi(table, count, total_blocks, 0, ST(stream));
+}
+
+int b200seg_unpack_wgrads_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,
+                                b200seg_stream stream) {
+  B200_CHECK_ARG(table != nullptr && count >= 0 && total_blocks >= 0, "b200seg_unpack_wgrads_multi: bad argument");
+  B200_DEVICE(device);
+  return ew_pack_multi(table, count, total_blocks, 1, ST(stream));
 }
 
 int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, int w_dtype, const float* bias,

@@ -55,14 +55,15 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t 
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 
+template <int CIN, int COUT, int KD>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  const int CP = p.Cin / 8;                                  // 8-channel planes
-  const uint32_t PLANE = HP_H * HP_W * 16u;                  // bytes of one plane of one slice
-  const uint32_t SLICE = (uint32_t)CP * PLANE;
-  const int taps = p.kd * 9;
-  const uint32_t W_BYTES = (uint32_t)taps * p.Cin * p.Cout * 2u;
+  constexpr int CP = CIN / 8;                                // 8-channel planes
+  constexpr uint32_t PLANE = HP_H * HP_W * 16u;              // bytes of one plane of one slice
+  constexpr uint32_t SLICE = (uint32_t)CP * PLANE;
+  constexpr int taps = KD * 9;
+  constexpr uint32_t W_BYTES = (uint32_t)taps * CIN * COUT * 2u;
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + ((W_BYTES + 127u) & ~127u);
   uint8_t* tail = s_ring + (size_t)p.nslices * SLICE;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int pd = p.kd / 2;
+  constexpr int pd = KD / 2;
 
   auto decode = [&](int item, int& n, int& h0, int& w0, int& d0, int& nd) {
     int t = item;
@@ -119,26 +120,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
 
   if (warp == 0) {
     // ===================================================== MMA issuer
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_lbo = p.swap_lbo_sbo ? HP_W * 16u : PLANE;
     const uint32_t a_sbo = p.swap_lbo_sbo ? PLANE : HP_W * 16u;
-    const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.Cout * 16u;
-    const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)p.Cout * 16u : 128u;
+    const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)COUT * 16u;
+    const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)COUT * 16u : 128u;
     const uint64_t a_hi = make_nosw_desc(0, a_lbo, a_sbo);
     const uint64_t b_hi = make_nosw_desc(0, b_lbo, b_sbo);
     const uint32_t ring_u32 = smem_u32(s_ring);
-    const uint32_t w_u32 = smem_u32(s_w);
-    const int kchunks = p.Cin / 16;
+    const uint64_t b_base = b_hi | (uint64_t)(smem_u32(s_w) >> 4);
+    constexpr int kchunks = CIN / 16;
     uint32_t gs = 0;   // slices consumed so far (ring position of the item's first slice)
     uint32_t go = 0;   // output slice-tiles produced so far
     for (int item = item_begin; item < item_end; ++item) {
       int n, h0, w0, d0, nd;
       decode(item, n, h0, w0, d0, nd);
-      const int nsl = nd + p.kd - 1;
+      const int nsl = nd + KD - 1;
       for (int o = 0; o < nd; ++o, ++go) {
-        // input slices o .. o+kd-1 of this item must have landed
-        const int first_wait = (o == 0) ? 0 : p.kd - 1;
-        for (int k = first_wait; k < p.kd; ++k) {
+        // input slices o .. o+KD-1 of this item must have landed
+        const int first_wait = (o == 0) ? 0 : KD - 1;
+        for (int k = first_wait; k < KD; ++k) {
           const uint32_t sl = gs + o + k;
           mbar_wait(&sfull[sl % p.nslices], (sl / p.nslices) & 1u);
         }
@@ -148,29 +149,30 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
         fence_proxy_async();
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t tacc = tmem_base + as * (uint32_t)p.Cout;
-          uint32_t first = 1;
-          for (int kd_ = 0; kd_ < p.kd; ++kd_) {
+          const uint32_t tacc = tmem_base + as * (uint32_t)COUT;
+          // straight-line issue: every descriptor is (per-slice base) + compile-time offset, in 16-byte units
+#pragma unroll
+          for (int kd_ = 0; kd_ < KD; ++kd_) {
             const uint32_t sl = gs + o + kd_;
-            const uint32_t sbase = ring_u32 + (sl % p.nslices) * SLICE;
+            const uint64_t a_base = a_hi | (uint64_t)((ring_u32 + (sl % p.nslices) * SLICE) >> 4);
+#pragma unroll
             for (int kh_ = 0; kh_ < 3; ++kh_)
-              for (int kw_ = 0; kw_ < 3; ++kw_) {
-                const int tap = (kd_ * 3 + kh_) * 3 + kw_;
+#pragma unroll
+              for (int kw_ = 0; kw_ < 3; ++kw_)
+#pragma unroll
                 for (int kc = 0; kc < kchunks; ++kc) {
-                  // descriptors differ only in the 14-bit start-address field (16-byte units, smem < 256 KB)
-                  const uint32_t a_addr = sbase + (uint32_t)(2 * kc) * PLANE + (uint32_t)(kh_ * HP_W + kw_) * 16u;
-                  const uint32_t b_addr = w_u32 + (uint32_t)((tap * kchunks + kc) * 2 * p.Cout) * 16u;
-                  umma_bf16(tacc, a_hi | (uint64_t)(a_addr >> 4), b_hi | (uint64_t)(b_addr >> 4), idesc,
-                            first ? 0u : 1u);
-                  first = 0;
+                  constexpr uint32_t dummy = 0;
+                  (void)dummy;
+                  const uint32_t a_off = ((uint32_t)(2 * kc) * PLANE + (uint32_t)(kh_ * HP_W + kw_) * 16u) >> 4;
+                  const uint32_t b_off = ((uint32_t)((((kd_ * 3 + kh_) * 3 + kw_) * kchunks + kc) * 2 * COUT) * 16u) >> 4;
+                  umma_bf16(tacc, a_base + a_off, b_base + b_off, idesc, (kd_ | kh_ | kw_ | kc) != 0 ? 1u : 0u);
                 }
-              }
           }
           umma_commit(&tfull[as]);
-          // input slice o is no longer needed; at the end of the item neither are the trailing kd-1
+          // input slice o is no longer needed; at the end of the item neither are the trailing KD-1
           umma_commit(&sempty[(gs + o) % p.nslices]);
           if (o == nd - 1)
-            for (int k = 1; k < p.kd; ++k) umma_commit(&sempty[(gs + o + k) % p.nslices]);
+            for (int k = 1; k < KD; ++k) umma_commit(&sempty[(gs + o + k) % p.nslices]);
         }
         __syncwarp();
       }
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
     int it_item = item_begin, it_i = 0, it_nsl = 0, n = 0, h0 = 0, w0 = 0, d0 = 0, nd = 0;
     if (it_item < item_end) {
       decode(it_item, n, h0, w0, d0, nd);
-      it_nsl = nd + p.kd - 1;
+      it_nsl = nd + KD - 1;
     }
     uint4 regs[kMaxPieces];
     auto issue_loads = [&]() {
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
           it_i = 0;
           if (it_item < item_end) {
             decode(it_item, n, h0, w0, d0, nd);
-            it_nsl = nd + p.kd - 1;
+            it_nsl = nd + KD - 1;
           }
         }
         ++sl;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
         it_i = 0;
         if (it_item < item_end) {
           decode(it_item, n, h0, w0, d0, nd);
-          it_nsl = nd + p.kd - 1;
+          it_nsl = nd + KD - 1;
         }
       }
       fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -412,7 +414,11 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   (void)kind;
   const int maxsm = tc_max_smem(device);
   if (device >= 0 && device < 64 && !g_halo_init[device]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+#define HALO_ATTR(CI, CO, K) \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CI, CO, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm))
+    HALO_ATTR(16, 16, 3); HALO_ATTR(16, 32, 3); HALO_ATTR(32, 16, 3); HALO_ATTR(32, 32, 3);
+    HALO_ATTR(16, 16, 1); HALO_ATTR(16, 32, 1); HALO_ATTR(32, 16, 1); HALO_ATTR(32, 32, 1);
+#undef HALO_ATTR
     g_halo_init[device] = 1;
   }
   HaloArgs p;
@@ -462,7 +468,19 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.cp_async = cpa;
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = sms < p.nitems ? sms : p.nitems;
-  conv_halo_kernel<<<grid, kHaloThreads, smem_bytes, st>>>(p);
+#define HALO_LAUNCH(CI, CO, K) conv_halo_kernel<CI, CO, K><<<grid, kHaloThreads, smem_bytes, st>>>(p)
+  if (p.kd == 3) {
+    if (p.Cin == 16 && p.Cout == 16) HALO_LAUNCH(16, 16, 3);
+    else if (p.Cin == 16) HALO_LAUNCH(16, 32, 3);
+    else if (p.Cout == 16) HALO_LAUNCH(32, 16, 3);
+    else HALO_LAUNCH(32, 32, 3);
+  } else {
+    if (p.Cin == 16 && p.Cout == 16) HALO_LAUNCH(16, 16, 1);
+    else if (p.Cin == 16) HALO_LAUNCH(16, 32, 1);
+    else if (p.Cout == 16) HALO_LAUNCH(32, 16, 1);
+    else HALO_LAUNCH(32, 32, 1);
+  }
+#undef HALO_LAUNCH
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

@@ -43,6 +43,67 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
   }
 }
 
+// Multi-tensor forms: one launch (re)packs every conv operand of a network / unpacks every weight gradient.
+// Each descriptor owns a contiguous range of thread blocks; a block finds its descriptor by binary search.
+struct PackDesc {            // mirrors b200seg_pack_desc (include/b200seg.h)
+  const float* src;
+  void* dst;
+  long long st, sk, sn2, sn1;
+  int out_dtype, T, K, N2, N1, flip;
+  int block_start, nblocks;
+};
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackDesc d = table[lo];
+  const long long total = (long long)d.T * d.K * d.N2 * d.N1;
+  const int b = blockIdx.x - d.block_start;
+  for (long long i = b * 256LL + threadIdx.x; i < total; i += (long long)d.nblocks * 256) {
+    const int n1 = (int)(i % d.N1);
+    long long r = i / d.N1;
+    const int n2 = (int)(r % d.N2);
+    r /= d.N2;
+    const int k = (int)(r % d.K);
+    const int t = (int)(r / d.K);
+    const int ts = d.flip ? (d.T - 1 - t) : t;
+    const float v = d.src[ts * d.st + k * d.sk + n2 * d.sn2 + n1 * d.sn1];
+    if (d.out_dtype == B200SEG_BF16) static_cast<bf16*>(d.dst)[i] = __float2bfloat16_rn(v);
+    else static_cast<float*>(d.dst)[i] = v;
+  }
+}
+
+// unpack: dst[t*st + k*sk + n*sn2] = src[(t*K + k)*N2 + n]   (N1 unused = 1)
+__global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackDesc d = table[lo];
+  const long long total = (long long)d.T * d.K * d.N2;
+  const int b = blockIdx.x - d.block_start;
+  float* out = static_cast<float*>(d.dst);
+  for (long long i = b * 256LL + threadIdx.x; i < total; i += (long long)d.nblocks * 256) {
+    const int n = (int)(i % d.N2);
+    const long long r = i / d.N2;
+    const int k = (int)(r % d.K);
+    const int t = (int)(r / d.K);
+    out[t * d.st + k * d.sk + n * d.sn2] = d.src[i];
+  }
+}
+
+int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack, cudaStream_t s) {
+  if (count <= 0 || total_blocks <= 0) return B200SEG_OK;
+  if (unpack) unpack_multi_kernel<<<total_blocks, 256, 0, s>>>(static_cast<const PackDesc*>(table_dev), count);
+  else pack_multi_kernel<<<total_blocks, 256, 0, s>>>(static_cast<const PackDesc*>(table_dev), count);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // GroupNorm finalize: stats (double sum, sumsq per (n,c)) -> A,B per (n,c); mean,rstd per (n,g)
 // ---------------------------------------------------------------------------------------------
@@ -129,45 +190,23 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
       B2[j] = 0.f;
     }
   }
-  for (; gi < total; gi += 2 * stride) {
-    // two voxel groups per trip, loads first
-    const long long gi2 = gi + stride;
-    const bool two = gi2 < total;
-    const long long vox0 = (long long)n * V + gi / G;
-    const long long vox1 = (long long)n * V + (two ? gi2 : gi) / G;
-    float a0[VEC], a1[VEC], b0[VEC], b1[VEC], r0[VEC], r1[VEC];
-    Vec<T, VEC>::load(y1 + vox0 * ld1 + c0, a0);
-    Vec<T, VEC>::load(y1 + vox1 * ld1 + c0, a1);
+  for (; gi < total; gi += stride) {
+    long long vox = (long long)n * V + gi / G;
+    float a[VEC], o[VEC];
+    Vec<T, VEC>::load(y1 + vox * ld1 + c0, a);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = fmaxf(fmaf(a[j], A1[j], B1[j]), 0.f);
     if (y2 != nullptr) {
-      Vec<T, VEC>::load(y2 + vox0 * ld2 + c0, b0);
-      Vec<T, VEC>::load(y2 + vox1 * ld2 + c0, b1);
+      Vec<T, VEC>::load(y2 + vox * ld2 + c0, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] += fmaxf(fmaf(a[j], A2[j], B2[j]), 0.f);
     }
     if (res != nullptr) {
-      Vec<T, VEC>::load(res + vox0 * ldr + c0, r0);
-      Vec<T, VEC>::load(res + vox1 * ldr + c0, r1);
-    }
-    float o0[VEC], o1[VEC];
+      Vec<T, VEC>::load(res + vox * ldr + c0, a);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      o0[j] = fmaxf(fmaf(a0[j], A1[j], B1[j]), 0.f);
-      o1[j] = fmaxf(fmaf(a1[j], A1[j], B1[j]), 0.f);
+      for (int j = 0; j < VEC; ++j) o[j] += a[j];
     }
-    if (y2 != nullptr) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        o0[j] += fmaxf(fmaf(b0[j], A2[j], B2[j]), 0.f);
-        o1[j] += fmaxf(fmaf(b1[j], A2[j], B2[j]), 0.f);
-      }
-    }
-    if (res != nullptr) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        o0[j] += r0[j];
-        o1[j] += r1[j];
-      }
-    }
-    Vec<T, VEC>::store(out + vox0 * ldo + c0, o0);
-    if (two) Vec<T, VEC>::store(out + vox1 * ldo + c0, o1);
+    Vec<T, VEC>::store(out + vox * ldo + c0, o);
   }
 }
 
@@ -186,47 +225,35 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_redd[i] = 0.0;
   __syncthreads();
   float A[VEC], B[VEC];
-  double s1[VEC], s2[VEC], s3[VEC];
+  float f1[VEC], f2[VEC], f3[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const float* p = coef + ((long long)n * C + c0 + j) * 2;
     A[j] = p[0];
     B[j] = p[1];
-    s1[j] = s2[j] = s3[j] = 0.0;
+    f1[j] = f2[j] = f3[j] = 0.f;
   }
-  // 4 voxel groups per trip: all 8 loads are issued before the first use (memory-level parallelism), their
-  // contributions are added in fp32 and flushed into the fp64 accumulators once per trip
-  for (; gi < total; gi += 4 * stride) {
-    float yv[4][VEC], gv[4][VEC];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long g2 = gi + u * stride;
-      if (g2 < total) {
-        const long long vox = (long long)n * V + g2 / G;
-        Vec<T, VEC>::load(y + vox * ldy + c0, yv[u]);
-        Vec<T, VEC>::load(g + vox * ldg + c0, gv[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          yv[u][j] = 0.f;
-          gv[u][j] = 0.f;
-        }
-      }
-    }
+  // a thread sees only ~10 voxel groups (grid sized to the chip): its partial sums stay in fp32, everything
+  // after that (cross-lane, cross-warp, cross-CTA) is accumulated in fp64
+  for (; gi < total; gi += stride) {
+    const long long vox = (long long)n * V + gi / G;
+    float yv[VEC], gv[VEC];
+    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
+    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      float f1 = 0.f, f2 = 0.f, f3 = 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float d = fmaf(yv[u][j], A[j], B[j]) > 0.f ? gv[u][j] : 0.f;
-        f1 += d;
-        f2 = fmaf(d, yv[u][j], f2);
-        f3 += yv[u][j];
-      }
-      s1[j] += (double)f1;
-      s2[j] += (double)f2;
-      s3[j] += (double)f3;
+      const float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] : 0.f;
+      f1[j] += d;
+      f2[j] = fmaf(d, yv[j], f2[j]);
+      f3[j] += yv[j];
     }
+  }
+  double s1[VEC], s2[VEC], s3[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    s1[j] = (double)f1[j];
+    s2[j] = (double)f2[j];
+    s3[j] = (double)f3[j];
   }
   // lanes l and l ^ off share the channel group when off is a multiple of G (G a power of two <= 16)
   const bool pow2 = (G & (G - 1)) == 0;
@@ -320,25 +347,17 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
     Q[j] = q[1];
     R[j] = q[2];
   }
-  for (; gi < total; gi += 2 * stride) {
-    const long long gi2 = gi + stride;
-    const bool two = gi2 < total;
-    const long long vox0 = (long long)n * V + gi / G;
-    const long long vox1 = (long long)n * V + (two ? gi2 : gi) / G;
-    float y0[VEC], y1v[VEC], g0[VEC], g1[VEC], o0[VEC], o1[VEC];
-    Vec<T, VEC>::load(y + vox0 * ldy + c0, y0);
-    Vec<T, VEC>::load(y + vox1 * ldy + c0, y1v);
-    Vec<T, VEC>::load(g + vox0 * ldg + c0, g0);
-    Vec<T, VEC>::load(g + vox1 * ldg + c0, g1);
+  for (; gi < total; gi += stride) {
+    long long vox = (long long)n * V + gi / G;
+    float yv[VEC], gv[VEC], o[VEC];
+    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
+    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const float d0 = fmaf(y0[j], A[j], B[j]) > 0.f ? g0[j] * P[j] : 0.f;
-      const float d1 = fmaf(y1v[j], A[j], B[j]) > 0.f ? g1[j] * P[j] : 0.f;
-      o0[j] = d0 + fmaf(y0[j], Q[j], R[j]);
-      o1[j] = d1 + fmaf(y1v[j], Q[j], R[j]);
+      float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] * P[j] : 0.f;
+      o[j] = d + fmaf(yv[j], Q[j], R[j]);
     }
-    Vec<T, VEC>::store(dy + vox0 * ldd + c0, o0);
-    if (two) Vec<T, VEC>::store(dy + vox1 * ldd + c0, o1);
+    Vec<T, VEC>::store(dy + vox * ldd + c0, o);
   }
 }
 

@@ -92,6 +92,8 @@ class Engine:
         self.need_grad = True
         self._z64 = None
         self._z32 = None
+        self._packs: Dict[Tuple[str, str], object] = {}
+        self._unpack_list: List[Tuple[Tensor, Tensor]] = []
 
     # ---------------------------------------------------------------- allocation helpers
     def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
@@ -120,11 +122,30 @@ class Engine:
         self._mi += 1
         return m
 
+    def _prepack(self, specs, need_grad: bool) -> None:
+        """ONE launch packs every conv operand of the step (forward and data-gradient layouts).
+        specs: [(wname, kind, vox_out, vox_in, needs_dgrad)]."""
+        reqs, keys = [], []
+        for wname, kind, vox_out, vox_in, dgrad in specs:
+            reqs.append((self.P[wname], kind, "fwd", self.T, self.dims, vox_out))
+            keys.append((wname, "fwd"))
+            if need_grad and dgrad:
+                reqs.append((self.P[wname], kind, "dgrad", self.T, self.dims, vox_in))
+                keys.append((wname, "dgrad"))
+        self._packs = dict(zip(keys, self.be.pack_many(reqs)))
+
+    def _finish_backward(self) -> None:
+        self.be.unpack_many(self._unpack_list)
+        self._unpack_list = []
+        self._packs = {}
+
     # ---------------------------------------------------------------- forward primitives
     def conv_raw(self, kind: int, wname: str, bname: Optional[str], x: Tensor, y: Tensor,
                  stats: Optional[Tensor] = None) -> None:
         w = self.P[wname]
-        wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims, vox=y.numel() // (y.shape[0] * y.shape[-1]))
+        wpk = self._packs.get((wname, "fwd"))
+        if wpk is None:
+            wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims, vox=y.numel() // (y.shape[0] * y.shape[-1]))
         bias = self.P[bname] if bname is not None else None
         self.be.conv(kind, self.dims, x, wpk, bias, y, stats, None)
 
@@ -202,10 +223,13 @@ class Engine:
         else:
             dwp = self.zeros((taps, cin, cout), torch.float32, dev)
             be.wgrad(L.kind, self.dims, L.x, dy, dwp)
-        be.unpack_wgrad(dwp, self._grad_view(L.wname), L.kind, self.dims)
+        self._unpack_list.append((dwp, self._grad_view(L.wname)))
         if not need_dx:
             return None
-        wd = be.pack_weight(w, L.kind, "dgrad", self.T, self.dims, vox=L.x.numel() // (L.x.shape[0] * L.x.shape[-1]))
+        wd = self._packs.get((L.wname, "dgrad"))
+        if wd is None:
+            wd = be.pack_weight(w, L.kind, "dgrad", self.T, self.dims,
+                                vox=L.x.numel() // (L.x.shape[0] * L.x.shape[-1]))
         dkind = {K3: K3, K1: K1, DOWN: UP, UP: DOWN}[L.kind]
         if dx_out is None:
             dx_out = torch.empty(L.x.shape, dtype=self.T, device=dev)
@@ -245,6 +269,17 @@ class Engine:
         # skip-concat buffers of the four UpTransitions: [up | skip], VNet3d.py:74
         cats = [self.new(x, sps[i], 2 * ch[i]) for i in range(4)]
         skips = [cats[i][..., ch[i]:] for i in range(4)]
+
+        vox = [sp[0] * sp[1] * sp[2] for sp in sps]
+        specs = [("in_tr.conv1.weight", K3, vox[0], vox[0], False), ("in_tr.conv2.weight", K1, vox[0], vox[0], False)]
+        for i, (name, nops) in enumerate((("down_tr32", 2), ("down_tr64", 3), ("down_tr128", 3), ("down_tr256", 3))):
+            specs.append((name + ".down_conv.weight", DOWN, vox[i + 1], vox[i], True))
+            specs += [(f"{name}.ops.{j}.conv1.weight", K3, vox[i + 1], vox[i + 1], True) for j in range(nops)]
+        for i, (name, nops) in zip((3, 2, 1, 0), (("up_tr256", 3), ("up_tr128", 3), ("up_tr64", 2), ("up_tr32", 1))):
+            specs.append((name + ".up_conv.weight", UP, vox[i], vox[i + 1], True))
+            specs.append((name + ".conv.weight", K1, vox[i], vox[i], True))
+            specs += [(f"{name}.ops.{j}.conv1.weight", K3, vox[i], vox[i], True) for j in range(nops)]
+        self._prepack(specs, need_grad)
 
         # ---- InputTransition3d (VNet3d.py:34-43): one bn1 serves both branches
         La = self.conv_gn(K3, "in_tr.conv1.weight", "in_tr.conv1.bias", "in_tr.bn1", xin, sp0, f)
@@ -324,6 +359,7 @@ class Engine:
         La, Lb = sv["in_tr"]
         self.bwd_layer(La, g, False)
         self.bwd_layer(Lb, g, False)
+        self._finish_backward()
         return flat
 
     # ================================================================== UNet3d / UNet2d
@@ -350,6 +386,17 @@ class Engine:
             s = sps[-1]
             sps.append((s[0] // 2 if dims == 3 else 1, s[1] // 2, s[2] // 2))
         cats = [self.new(x, sps[i], 2 * ch[i]) for i in range(4)]
+        vox = [sp[0] * sp[1] * sp[2] for sp in sps]
+        specs = []
+        for i, (mod, name) in enumerate((("encoder1", "enc1"), ("encoder2", "enc2"), ("encoder3", "enc3"),
+                                         ("encoder4", "enc4"), ("bottleneck", "bottleneck"))):
+            specs.append((f"{mod}.{name}conv1.weight", K3, vox[i], vox[i], i > 0))
+            specs.append((f"{mod}.{name}conv2.weight", K3, vox[i], vox[i], True))
+        for i in (3, 2, 1, 0):
+            specs.append((f"upconv{i + 1}.weight", UP, vox[i], vox[i + 1], True))
+            specs.append((f"decoder{i + 1}.dec{i + 1}conv1.weight", K3, vox[i], vox[i], True))
+            specs.append((f"decoder{i + 1}.dec{i + 1}conv2.weight", K3, vox[i], vox[i], True))
+        self._prepack(specs, need_grad)
 
         def block(mod: str, name: str, h: Tensor, sp, co: int, dst: Tensor):
             L1 = self.conv_gn(K3, f"{mod}.{name}conv1.weight", None, f"{mod}.{name}norm1", h, sp, co)
@@ -404,4 +451,5 @@ class Engine:
             L1, L2 = sv[f"encoder{i + 1}"]
             g1 = self.bwd_layer(L2, ge, True)
             g = self.bwd_layer(L1, g1, i > 0)
+        self._finish_backward()
         return flat

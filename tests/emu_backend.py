@@ -54,6 +54,13 @@ class EmuBackend:
                 pk = w3.permute(2, 1, 0)
         return pk.contiguous().to(dtype)
 
+    def pack_many(self, reqs):
+        return [self.pack_weight(w, kind, which, dtype, dims, vox=vox) for (w, kind, which, dtype, dims, vox) in reqs]
+
+    def unpack_many(self, items):
+        for dwp, grad in items:
+            grad.copy_(dwp.permute(2, 1, 0).reshape(grad.shape))
+
     def unpack_wgrad(self, dwp, grad, kind, dims):
         """dwp: gather kinds [t][ci][co] -> grad (Co,Ci,t...) ; UP: [t][co][ci] -> grad (Ci,Co,t...)."""
         grad.copy_(dwp.permute(2, 1, 0).reshape(grad.shape))
