@@ -127,20 +127,20 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         const int id = t % p.td;
         const int n = t / p.td;
         const int w0 = iw * p.bw * p.sw, h0 = ih * p.bh * p.sh, d0 = id * p.bd * p.sd;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int kw_ = tap % p.kw;
-          const int kh_ = (tap / p.kw) % p.kh;
-          const int kd_ = tap / (p.kw * p.kh);
-          for (int cb = 0; cb < cblocks; ++cb, ++it) {
-            const uint32_t s = it % p.nstages;
-            const uint32_t ph = (it / p.nstages) & 1u;
-            mbar_wait(&empty[s], ph ^ 1u);
-            uint8_t* sa = smem + (size_t)s * STAGE;
-            mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
-            tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
-            tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout);
-          }
-        }
+        int tap = 0;
+        for (int kd_ = 0; kd_ < p.kd; ++kd_)
+          for (int kh_ = 0; kh_ < p.kh; ++kh_)
+            for (int kw_ = 0; kw_ < p.kw; ++kw_, ++tap) {
+              for (int cb = 0; cb < cblocks; ++cb, ++it) {
+                const uint32_t s = it % p.nstages;
+                const uint32_t ph = (it / p.nstages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                uint8_t* sa = smem + (size_t)s * STAGE;
+                mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
+                tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
+                tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout);
+              }
+            }
       }
     }
   } else if (warp == 1) {

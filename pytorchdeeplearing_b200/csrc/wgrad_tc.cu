@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   uint64_t* empty = full + kWgMaxStages;
   uint64_t* tfull = empty + kWgMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+  int4* s_sub = reinterpret_cast<int4*>(tmem_slot + 4);       // [mb_per_cta][128/CA] : channel, dw, dh, dd of a sub-tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,6 +72,20 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // tap decode of every A sub-tile this CTA will ever load (keeps integer division out of the producer loop)
+  for (int i = threadIdx.x; i < nmb * nasub; i += blockDim.x) {
+    const int mb = i / nasub, j = i - mb * nasub;
+    const int R = (mb0 + mb) * 128 + j * p.CA;
+    int4 e = make_int4(-1, 0, 0, 0);
+    if (R < p.Rtot) {
+      const int tap = R / p.Ka;
+      e.x = R - tap * p.Ka;
+      e.y = tap % p.kw - p.pw;
+      e.z = (tap / p.kw) % p.kh - p.ph;
+      e.w = tap / (p.kw * p.kh) - p.pd;
+    }
+    s_sub[i] = e;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -93,19 +108,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           const uint32_t ph = (it / p.nstages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * STAGE;
-          // count the sub-tiles that exist (the last M block of the last tap group may be partial)
+          // the last M block may be partial: skip (and do not expect) the sub-tiles that do not exist
           int valid = 0;
-          for (int j = 0; j < nasub; ++j)
-            if ((mb0 + mb) * 128 + j * p.CA < p.Rtot) ++valid;
+          for (int j = 0; j < nasub; ++j) valid += s_sub[mb * nasub + j].x >= 0 ? 1 : 0;
           mbar_expect_tx(&full[s], (uint32_t)valid * A_SUB + B_BYTES);
           for (int j = 0; j < valid; ++j) {
-            const int R = (mb0 + mb) * 128 + j * p.CA;
-            const int tap = R / p.Ka, ch = R - tap * p.Ka;
-            const int kw_ = tap % p.kw;
-            const int kh_ = (tap / p.kw) % p.kh;
-            const int kd_ = tap / (p.kw * p.kh);
-            tma_load_5d(&tmA, sa + (size_t)j * A_SUB, &full[s], ch, w0 * p.sw + kw_ - p.pw, h0 * p.sh + kh_ - p.ph,
-                        d0 * p.sd + kd_ - p.pd, n);
+            const int4 e = s_sub[mb * nasub + j];
+            tma_load_5d(&tmA, sa + (size_t)j * A_SUB, &full[s], e.x, w0 * p.sw + e.y, h0 * p.sh + e.z, d0 * p.sd + e.w, n);
           }
           for (uint32_t j = 0; j < nbsub; ++j)
             tma_load_5d(&tmB, sa + A_BYTES + (size_t)j * B_SUB, &full[s], (int)j * p.CB, w0, h0, d0, n);
@@ -251,7 +260,7 @@ int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* 
   while (cols < p.mb_per_cta * p.Kb) cols *= 2;
   p.tmem_cols = cols;
   const uint32_t stage = 128u * 128u * 2u + 128u * (uint32_t)p.Kb * 2u;
-  const uint32_t tail = (2 * kWgMaxStages + 2) * 8 + 16;
+  const uint32_t tail = (2 * kWgMaxStages + 2) * 8 + 16 + 16 + (uint32_t)(p.mb_per_cta * (128 / p.CA)) * 16;
   const int maxsm = tc_max_smem(device);
   int nst = (int)((maxsm - 1024 - (int)tail - 256) / (int)stage);
   if (nst > kWgMaxStages) nst = kWgMaxStages;

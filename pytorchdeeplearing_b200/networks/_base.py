@@ -16,11 +16,10 @@ class _SegNetFunction(torch.autograd.Function):
     Backward runs on the autograd thread; every kernel launch takes device+stream explicitly."""
 
     @staticmethod
-    def forward(ctx, mod, x, masks, *params):
+    def forward(ctx, mod, need_grad, x, masks, *params):
         be = runtime.get_backend(x)
         eng = Engine(be, runtime.act_dtype(), mod._dims)
         P = dict(zip(mod._pnames, [p.detach() for p in params]))
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         xx = x.detach()
         if xx.dtype != torch.float32:
             xx = xx.float()
@@ -46,7 +45,7 @@ class _SegNetFunction(torch.autograd.Function):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         grads = [eng.grads[n] for n in ctx.names]
         ctx.eng = None
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 class SegNetBase(nn.Module):
@@ -86,7 +85,9 @@ class SegNetBase(nn.Module):
                                    f"{tuple(x.shape[2:])}")
         params = [p for _, p in self.named_parameters()]
         masks = self._draw_masks(x)
-        return _SegNetFunction.apply(self, x, masks, *params)
+        # (grad mode is always off inside Function.forward, so the decision is taken here)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _SegNetFunction.apply(self, need_grad, x, masks, *params)
 
 
 class _Holder(nn.Module):
