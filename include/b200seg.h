@@ -124,6 +124,27 @@ int b200seg_gn_finalize(const double* stats, const float* gamma, const float* be
 /* out = relu(y1*A1+B1) [+ relu(y2*A2+B2)] [+ res]   (torch.add residuals VNet3d.py:41,58,79) */
 int b200seg_apply(const b200seg_tensor* y1, const float* coef1, const b200seg_tensor* y2, const float* coef2,
                   const b200seg_tensor* res, const b200seg_tensor* out, int device, b200seg_stream stream);
+/* Fused-coefficient forms: the kernels derive A, B (and the backward P, Q, R, d gamma, d beta, d bias) for their
+ * own channels from the fp64 statistics, so no finalize launches are needed.  `b200seg_gn` names one GroupNorm
+ * application: statistics [N][C][2] written by b200seg_conv, affine parameters, optional dropout scale [N][C]. */
+typedef struct b200seg_gn {
+  const double* stats;
+  const float* gamma;
+  const float* beta;
+  const float* scale;
+  int32_t groups;
+  int64_t vox;     /* voxels per sample of the normalised tensor */
+  float eps;
+} b200seg_gn;
+int b200seg_apply_gn(const b200seg_tensor* y1, const b200seg_gn* gn1, const b200seg_tensor* y2, const b200seg_gn* gn2,
+                     const b200seg_tensor* res, const b200seg_tensor* out, int device, b200seg_stream stream);
+int b200seg_gn_bwd_reduce_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
+                             int device, b200seg_stream stream);
+/* dy as b200seg_gn_bwd_apply; additionally dgamma[c] +=, dbeta[c] +=, dbias[c] = (dbias may be NULL) */
+int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, const double* sums,
+                            const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int device,
+                            b200seg_stream stream);
+
 /* native_group_norm_backward + threshold_backward + dropout backward:
  *   sums[n][c] += { sum g*m, sum g*m*y, sum y },  m = [y*A+B > 0] */
 int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums,

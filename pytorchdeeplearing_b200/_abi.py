@@ -31,7 +31,13 @@ class PackDesc(C.Structure):   # include/b200seg.h: struct b200seg_pack_desc
                 ("N1", C.c_int32), ("flip", C.c_int32), ("block_start", C.c_int32), ("nblocks", C.c_int32)]
 
 
+class GnDesc(C.Structure):     # include/b200seg.h: struct b200seg_gn
+    _fields_ = [("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("scale", C.c_void_p),
+                ("groups", C.c_int32), ("vox", C.c_int64), ("eps", C.c_float)]
+
+
 _PT = C.POINTER(TensorDesc)
+_PG = C.POINTER(GnDesc)
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 _SIGNATURES = {
@@ -48,6 +54,9 @@ _SIGNATURES = {
     "b200seg_wgrad": ([_i, _i, _PT, _PT, _vp, _i, _vp], C.c_int),
     "b200seg_gn_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_apply": ([_PT, _vp, _PT, _vp, _PT, _PT, _i, _vp], C.c_int),
+    "b200seg_apply_gn": ([_PT, _PG, _PT, _PG, _PT, _PT, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_reduce_gn": ([_PT, _PT, _PG, _vp, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_apply_gn": ([_PT, _PT, _PG, _vp, _PT, _vp, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_reduce": ([_PT, _PT, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_apply": ([_PT, _PT, _vp, _vp, _PT, _i, _vp], C.c_int),
@@ -302,6 +311,35 @@ class CudaBackend:
         dev, st = self._ds(y1)
         d1, d2, dr, do = _desc(y1), _desc(y2), _desc(res), _desc(out)
         self._check(self.lib.b200seg_apply(C.byref(d1), c1.data_ptr(), _ref(d2), _p(c2), _ref(dr), C.byref(do), dev, st))
+
+    # fused-coefficient forms: gn = (stats, gamma, beta, scale|None, vox, groups, eps)
+    fused_gn = True
+
+    @staticmethod
+    def _gn(gn):
+        if gn is None:
+            return None
+        stats, gamma, beta, scale, vox, groups, eps = gn
+        return GnDesc(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(scale), groups, vox, eps)
+
+    def apply_gn(self, y1, gn1, y2, gn2, res, out):
+        dev, st = self._ds(y1)
+        d1, d2, dr, do = _desc(y1), _desc(y2), _desc(res), _desc(out)
+        g1, g2 = self._gn(gn1), self._gn(gn2)
+        self._check(self.lib.b200seg_apply_gn(C.byref(d1), C.byref(g1), _ref(d2), _ref(g2), _ref(dr), C.byref(do),
+                                              dev, st))
+
+    def gn_bwd_reduce_gn(self, g, y, gn, sums):
+        dev, st = self._ds(y)
+        dg, dy, gg = _desc(g), _desc(y), self._gn(gn)
+        self._check(self.lib.b200seg_gn_bwd_reduce_gn(C.byref(dg), C.byref(dy), C.byref(gg), sums.data_ptr(), dev, st))
+
+    def gn_bwd_apply_gn(self, g, y, gn, sums, dy, dgamma, dbeta, dbias):
+        dev, st = self._ds(y)
+        dg, dyy, dd, gg = _desc(g), _desc(y), _desc(dy), self._gn(gn)
+        self._check(self.lib.b200seg_gn_bwd_apply_gn(C.byref(dg), C.byref(dyy), C.byref(gg), sums.data_ptr(),
+                                                     C.byref(dd), dgamma.data_ptr(), dbeta.data_ptr(), _p(dbias),
+                                                     dev, st))
 
     def gn_bwd_reduce(self, g, y, coef, sums):
         dev, st = self._ds(y)

@@ -53,14 +53,16 @@ int ew_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, long lon
 int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack, cudaStream_t s);
 int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
                    int groups, long long vox, float eps, float* coef, float* mr, cudaStream_t s);
-int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_tensor* y2, const float* c2,
-             const b200seg_tensor* res, const b200seg_tensor* out, int device, cudaStream_t s);
-int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,
-                     cudaStream_t s);
+int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, const b200seg_tensor* y2,
+             const float* c2, const b200seg_gn* g2, const b200seg_tensor* res, const b200seg_tensor* out, int device,
+             cudaStream_t s);
+int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const b200seg_gn* gn,
+                     double* sums, int device, cudaStream_t s);
 int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
                        int groups, long long vox, float* coef3, float* dgamma, float* dbeta, float* dbias,
                        cudaStream_t s);
 int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
+                    const b200seg_gn* gn, const double* sums, float* dgamma, float* dbeta, float* dbias,
                     const b200seg_tensor* dy, int device, cudaStream_t s);
 int ew_colsum(const b200seg_tensor* dy, float* out, int device, cudaStream_t s);
 int ew_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, int device, cudaStream_t s);
@@ -192,7 +194,42 @@ int b200seg_apply(const b200seg_tensor* y1, const float* coef1, const b200seg_te
   OPT_TENSOR(res, "res");
   B200_CHECK_ARG(coef1 && (!y2 || coef2), "b200seg_apply: missing coefficients");
   B200_DEVICE(device);
-  return ew_apply(y1, coef1, y2, coef2, res, out, device, ST(stream));
+  return ew_apply(y1, coef1, nullptr, y2, coef2, nullptr, res, out, device, ST(stream));
+}
+
+static bool valid_gn(const b200seg_gn* g, int C) {
+  return g && g->stats && g->gamma && g->beta && g->groups > 0 && (C % g->groups) == 0 && g->vox > 0;
+}
+
+int b200seg_apply_gn(const b200seg_tensor* y1, const b200seg_gn* gn1, const b200seg_tensor* y2, const b200seg_gn* gn2,
+                     const b200seg_tensor* res, const b200seg_tensor* out, int device, b200seg_stream stream) {
+  REQ_TENSOR(y1, "y1");
+  REQ_TENSOR(out, "out");
+  OPT_TENSOR(y2, "y2");
+  OPT_TENSOR(res, "res");
+  B200_CHECK_ARG(valid_gn(gn1, y1->c) && (!y2 || valid_gn(gn2, y2->c)), "b200seg_apply_gn: bad GroupNorm reference");
+  B200_DEVICE(device);
+  return ew_apply(y1, nullptr, gn1, y2, nullptr, gn2, res, out, device, ST(stream));
+}
+
+int b200seg_gn_bwd_reduce_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
+                             int device, b200seg_stream stream) {
+  REQ_TENSOR(g, "g");
+  REQ_TENSOR(y, "y");
+  B200_CHECK_ARG(valid_gn(gn, y->c) && sums && y->c <= 2048, "b200seg_gn_bwd_reduce_gn: bad argument");
+  B200_DEVICE(device);
+  return ew_gn_bwd_reduce(g, y, nullptr, gn, sums, device, ST(stream));
+}
+
+int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, const double* sums,
+                            const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int device,
+                            b200seg_stream stream) {
+  REQ_TENSOR(g, "g");
+  REQ_TENSOR(y, "y");
+  REQ_TENSOR(dy, "dy");
+  B200_CHECK_ARG(valid_gn(gn, y->c) && sums && dgamma && dbeta, "b200seg_gn_bwd_apply_gn: bad argument");
+  B200_DEVICE(device);
+  return ew_gn_bwd_apply(g, y, nullptr, nullptr, gn, sums, dgamma, dbeta, dbias, dy, device, ST(stream));
 }
 
 int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,
@@ -202,7 +239,7 @@ int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, cons
   B200_CHECK_ARG(coef && sums, "b200seg_gn_bwd_reduce: null argument");
   B200_CHECK_ARG(y->c <= 4096, "b200seg_gn_bwd_reduce: too many channels");
   B200_DEVICE(device);
-  return ew_gn_bwd_reduce(g, y, coef, sums, device, ST(stream));
+  return ew_gn_bwd_reduce(g, y, coef, nullptr, sums, device, ST(stream));
 }
 
 int b200seg_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
@@ -221,7 +258,7 @@ int b200seg_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const
   REQ_TENSOR(dy, "dy");
   B200_CHECK_ARG(coef && coef3, "b200seg_gn_bwd_apply: null coefficients");
   B200_DEVICE(device);
-  return ew_gn_bwd_apply(g, y, coef, coef3, dy, device, ST(stream));
+  return ew_gn_bwd_apply(g, y, coef, coef3, nullptr, nullptr, nullptr, nullptr, nullptr, dy, device, ST(stream));
 }
 
 int b200seg_colsum(const b200seg_tensor* dy, float* out, int device, b200seg_stream stream) {

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
                 uint8_t* sa = smem + (size_t)s * STAGE;
                 mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
                 tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
-                tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout);
+                tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout + ng * p.Ntile);
               }
             }
       }
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       for (int cc = 0; cc < p.Ntile; cc += 16) {
         float v[16];
         tmem_ld16(tacc + (uint32_t)cc, v);
-        // channel block of this 16-column chunk (UP: columns are (tap, cout))
-        int c0 = cc;
+        // channel block of this 16-column chunk (UP: columns are (tap, cout); otherwise column group ng of Cout)
+        int c0 = ng * p.Ntile + cc;
         long long ovox = vox;
         if (p.up) {
           const int col = ng * p.Ntile + cc;
@@ -393,6 +393,18 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const int ncols = g.up ? g.ud * g.uh * g.uw * p.Cout : p.Cout;
   p.Ntile = ncols > 256 ? 256 : ncols;
   p.ngroups = ncols / p.Ntile;
+  {
+    // few voxel tiles (deep, small levels): split the output channels over more CTAs so the whole chip works
+    // on the layer; every group re-reads the activation tile (cheap, it is L2 resident) but only its own weights
+    int bw_, bh_, bd_;
+    tc_pick_box(p.W, p.H, p.D, &bw_, &bh_, &bd_);
+    const int tiles = p.N * ((p.W + bw_ - 1) / bw_) * ((p.H + bh_ - 1) / bh_) * ((p.D + bd_ - 1) / bd_);
+    const int sms = num_sms(device);
+    while (!g.up && tiles * p.ngroups * 2 <= sms && p.Ntile >= 64 && (p.Ntile / 2) % 16 == 0) {
+      p.Ntile /= 2;
+      p.ngroups *= 2;
+    }
+  }
   tc_pick_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd);
   p.tw = (p.W + p.bw - 1) / p.bw;
   p.th = (p.H + p.bh - 1) / p.bh;

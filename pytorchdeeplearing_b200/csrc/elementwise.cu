@@ -136,6 +136,90 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused GroupNorm coefficients: instead of separate finalize launches, every kernel that applies the
+// norm (forward apply, backward mask / dy) derives A, B (and mean, rstd) for its own channels straight
+// from the fp64 statistics -- same code everywhere, so forward and backward see bit-identical values.
+// ---------------------------------------------------------------------------------------------
+struct GnRef {
+  const double* stats;     // [N][C][2]  (null -> use the precomputed coefficient array instead)
+  const float* gamma;
+  const float* beta;
+  const float* scale;      // [N][C] dropout scale or null
+  int groups;
+  double m;                // elements per group = (C/groups) * voxels
+  float eps;
+};
+
+template <int VEC>
+__device__ __forceinline__ void gn_coef_from_stats(const GnRef& r, int n, int C, int c0, float* A, float* B,
+                                                   double* MU, double* RS) {
+  const int cpg = C / r.groups;
+  int last_g = -1;
+  double mean = 0.0, rstd = 0.0;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    if (g != last_g) {
+      double s = 0.0, q = 0.0;
+      for (int k = 0; k < cpg; ++k) {
+        const double* p = r.stats + ((long long)n * C + g * cpg + k) * 2;
+        s += p[0];
+        q += p[1];
+      }
+      mean = s / r.m;
+      double var = q / r.m - mean * mean;
+      if (var < 0.0) var = 0.0;
+      rstd = rsqrt(var + (double)r.eps);
+      last_g = g;
+    }
+    const double sc = r.scale ? (double)r.scale[(long long)n * C + c] : 1.0;
+    const double ga = r.gamma[c], be = r.beta[c];
+    A[j] = (float)(rstd * ga * sc);
+    B[j] = (float)((be - mean * rstd * ga) * sc);
+    if (MU) MU[j] = mean;
+    if (RS) RS[j] = rstd;
+  }
+}
+
+// P, Q, R of  dy = g*m*P + y*Q + R  for the thread's channels, from the backward sums
+template <int VEC>
+__device__ __forceinline__ void gn_bwd_coef_from_sums(const GnRef& r, const double* __restrict__ sums, int n, int C,
+                                                      int c0, const double* MU, const double* RS, float* P, float* Q,
+                                                      float* R, double* QD = nullptr, double* RD = nullptr) {
+  const int cpg = C / r.groups;
+  int last_g = -1;
+  double m1 = 0.0, m2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    const double mu = MU[j], rs = RS[j];
+    if (g != last_g) {
+      double sa = 0.0, sax = 0.0;
+      for (int k = 0; k < cpg; ++k) {
+        const int ck = g * cpg + k;
+        const double sk = r.scale ? (double)r.scale[(long long)n * C + ck] : 1.0;
+        const double* p = sums + ((long long)n * C + ck) * 3;
+        const double s1 = p[0] * sk, s2 = p[1] * sk;
+        const double gk = r.gamma[ck];
+        sa += gk * s1;
+        sax += gk * rs * (s2 - mu * s1);
+      }
+      m1 = sa / r.m;
+      m2 = sax / r.m;
+      last_g = g;
+    }
+    const double sc = r.scale ? (double)r.scale[(long long)n * C + c] : 1.0;
+    P[j] = (float)(rs * (double)r.gamma[c] * sc);
+    Q[j] = (float)(-rs * rs * m2);
+    R[j] = (float)(-rs * m1 + rs * rs * mu * m2);
+    if (QD) QD[j] = -rs * rs * m2;
+    if (RD) RD[j] = -rs * m1 + rs * rs * mu * m2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // vector helpers: VEC channels of type T <-> float[VEC]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int VEC> struct Vec;
@@ -173,21 +257,33 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
                                                     const float* __restrict__ coef1, const T* __restrict__ y2,
                                                     long long ld2, const float* __restrict__ coef2,
                                                     const T* __restrict__ res, long long ldr, T* __restrict__ out,
-                                                    long long ldo, int C, long long V) {
+                                                    long long ldo, int C, long long V, const GnRef gn1,
+                                                    const GnRef gn2) {
   EW_PROLOGUE(C)
   float A1[VEC], B1[VEC], A2[VEC], B2[VEC];
+  if (gn1.stats != nullptr) {
+    gn_coef_from_stats<VEC>(gn1, n, C, c0, A1, B1, nullptr, nullptr);
+  } else {
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const float* p = coef1 + ((long long)n * C + c0 + j) * 2;
-    A1[j] = p[0];
-    B1[j] = p[1];
-    if (y2 != nullptr) {
-      const float* q = coef2 + ((long long)n * C + c0 + j) * 2;
-      A2[j] = q[0];
-      B2[j] = q[1];
-    } else {
-      A2[j] = 0.f;
-      B2[j] = 0.f;
+    for (int j = 0; j < VEC; ++j) {
+      const float* p = coef1 + ((long long)n * C + c0 + j) * 2;
+      A1[j] = p[0];
+      B1[j] = p[1];
+    }
+  }
+  if (y2 != nullptr && gn2.stats != nullptr) {
+    gn_coef_from_stats<VEC>(gn2, n, C, c0, A2, B2, nullptr, nullptr);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (y2 != nullptr) {
+        const float* q = coef2 + ((long long)n * C + c0 + j) * 2;
+        A2[j] = q[0];
+        B2[j] = q[1];
+      } else {
+        A2[j] = 0.f;
+        B2[j] = 0.f;
+      }
     }
   }
   for (; gi < total; gi += stride) {
@@ -219,18 +315,22 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict__ g, long long ldg,
                                                             const T* __restrict__ y, long long ldy,
                                                             const float* __restrict__ coef,
-                                                            double* __restrict__ sums, int C, long long V) {
+                                                            double* __restrict__ sums, int C, long long V,
+                                                            const GnRef gn) {
   EW_PROLOGUE(C)
   extern __shared__ double s_redd[];   // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_redd[i] = 0.0;
   __syncthreads();
   float A[VEC], B[VEC];
   float f1[VEC], f2[VEC], f3[VEC];
+  if (gn.stats != nullptr) gn_coef_from_stats<VEC>(gn, n, C, c0, A, B, nullptr, nullptr);
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    const float* p = coef + ((long long)n * C + c0 + j) * 2;
-    A[j] = p[0];
-    B[j] = p[1];
+    if (gn.stats == nullptr) {
+      const float* p = coef + ((long long)n * C + c0 + j) * 2;
+      A[j] = p[0];
+      B[j] = p[1];
+    }
     f1[j] = f2[j] = f3[j] = 0.f;
   }
   // a thread sees only ~10 voxel groups (grid sized to the chip): its partial sums stay in fp32, everything
@@ -334,18 +434,50 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
                                                            const T* __restrict__ y, long long ldy,
                                                            const float* __restrict__ coef,
                                                            const float* __restrict__ coef3, T* __restrict__ dy,
-                                                           long long ldd, int C, long long V) {
+                                                           long long ldd, int C, long long V, const GnRef gn,
+                                                           const double* __restrict__ sums, int N,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ dbias) {
   EW_PROLOGUE(C)
   float A[VEC], B[VEC], P[VEC], Q[VEC], R[VEC];
+  if (gn.stats != nullptr) {
+    double MU[VEC], RS[VEC];
+    gn_coef_from_stats<VEC>(gn, n, C, c0, A, B, MU, RS);
+    gn_bwd_coef_from_sums<VEC>(gn, sums, n, C, c0, MU, RS, P, Q, R);
+    // parameter gradients (d gamma, d beta, d bias): one block, fixed order over the samples
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      const int cpg = C / gn.groups;
+      const double vox = gn.m / (double)cpg;
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double dg = 0.0, db = 0.0, dbi = 0.0;
+        for (int nn = 0; nn < N; ++nn) {
+          float a1[1], b1[1], p1[1], q1[1], r1[1];
+          double mu1[1], rs1[1], qd[1], rd[1];
+          gn_coef_from_stats<1>(gn, nn, C, c, a1, b1, mu1, rs1);
+          gn_bwd_coef_from_sums<1>(gn, sums, nn, C, c, mu1, rs1, p1, q1, r1, qd, rd);
+          const double sc = gn.scale ? (double)gn.scale[(long long)nn * C + c] : 1.0;
+          const double* sp = sums + ((long long)nn * C + c) * 3;
+          const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
+          db += s1;
+          dg += rs1[0] * (s2 - mu1[0] * s1);
+          dbi += rs1[0] * (double)gn.gamma[c] * s1 + qd[0] * s3 + rd[0] * vox;
+        }
+        dgamma[c] += (float)dg;
+        dbeta[c] += (float)db;
+        if (dbias != nullptr) dbias[c] = (float)dbi;
+      }
+    }
+  } else {
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const float* p = coef + ((long long)n * C + c0 + j) * 2;
-    A[j] = p[0];
-    B[j] = p[1];
-    const float* q = coef3 + ((long long)n * C + c0 + j) * 3;
-    P[j] = q[0];
-    Q[j] = q[1];
-    R[j] = q[2];
+    for (int j = 0; j < VEC; ++j) {
+      const float* p = coef + ((long long)n * C + c0 + j) * 2;
+      A[j] = p[0];
+      B[j] = p[1];
+      const float* q = coef3 + ((long long)n * C + c0 + j) * 3;
+      P[j] = q[0];
+      Q[j] = q[1];
+      R[j] = q[2];
+    }
   }
   for (; gi < total; gi += stride) {
     long long vox = (long long)n * V + gi / G;
@@ -575,8 +707,21 @@ int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, c
   return B200SEG_OK;
 }
 
-int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_tensor* y2, const float* c2,
-             const b200seg_tensor* res, const b200seg_tensor* out, int device, cudaStream_t s) {
+static GnRef make_gnref(const b200seg_gn* g, int C) {
+  GnRef r;
+  if (g == nullptr || g->stats == nullptr) {
+    r.stats = nullptr; r.gamma = nullptr; r.beta = nullptr; r.scale = nullptr; r.groups = 1; r.m = 1.0; r.eps = 0.f;
+    return r;
+  }
+  r.stats = g->stats; r.gamma = g->gamma; r.beta = g->beta; r.scale = g->scale; r.groups = g->groups;
+  r.m = (double)(C / g->groups) * (double)g->vox;
+  r.eps = g->eps;
+  return r;
+}
+
+int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, const b200seg_tensor* y2,
+             const float* c2, const b200seg_gn* g2, const b200seg_tensor* res, const b200seg_tensor* out, int device,
+             cudaStream_t s) {
   B200_CHECK_ARG(same_geom(y1, out) && (!y2 || same_geom(y2, out)) && (!res || same_geom(res, out)),
                  "apply: shape mismatch");
   B200_CHECK_ARG(y1->dtype == out->dtype && (!y2 || y2->dtype == out->dtype) && (!res || res->dtype == out->dtype),
@@ -589,14 +734,15 @@ int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_tensor* y2
     dim3 grid(ew_blocks(V, G, out->n, device), out->n);
     apply_kernel<T, VEC><<<grid, 256, 0, s>>>(
         static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
-        res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V);
+        res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V,
+        make_gnref(g1, C), make_gnref(g2, C));
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
-int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,
-                     cudaStream_t s) {
+int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const b200seg_gn* gn,
+                     double* sums, int device, cudaStream_t s) {
   B200_CHECK_ARG(same_geom(g, y) && g->dtype == y->dtype, "gn_bwd_reduce: g/y mismatch");
   const bool vok = vec_ok(g) && vec_ok(y);
   const long long V = nvox(y);
@@ -605,7 +751,8 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
     gn_bwd_reduce_kernel<T, VEC><<<grid, 256, 3 * C * sizeof(double), s>>>(
-        static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V);
+        static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
+        make_gnref(gn, C));
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -623,6 +770,7 @@ int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, 
 }
 
 int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
+                    const b200seg_gn* gn, const double* sums, float* dgamma, float* dbeta, float* dbias,
                     const b200seg_tensor* dy, int device, cudaStream_t s) {
   B200_CHECK_ARG(same_geom(g, y) && same_geom(dy, y) && g->dtype == y->dtype && dy->dtype == y->dtype,
                  "gn_bwd_apply: tensor mismatch");
@@ -634,7 +782,8 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
     gn_bwd_apply_kernel<T, VEC><<<grid, 256, 0, s>>>(static_cast<const T*>(g->ptr), g->ld,
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
-                                                     static_cast<T*>(dy->ptr), dy->ld, C, V);
+                                                     static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
+                                                     y->n, dgamma, dbeta, dbias);
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;

@@ -387,7 +387,7 @@ template <typename TA, typename TB>
 static int smallcin_wgrad_typed(const ConvGeom& g, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp,
                                 int device, cudaStream_t st) {
   const long long NV = (long long)b->n * b->d * b->h * b->w;
-  long long ctas = (long long)num_sms(device) * 4;
+  long long ctas = (long long)num_sms(device) * 16;   // many small CTAs: the per-tile staging latency overlaps across CTAs
   long long chunk = (NV + ctas - 1) / ctas;
   chunk = ((chunk + 127) / 128) * 128;
   if (chunk < 128) chunk = 128;

@@ -42,8 +42,9 @@ class Layer:
     gname: Optional[str]            # GroupNorm prefix ("in_tr.bn1") or None
     x: Tensor = None                # input activation view (N,D,H,W,Cin)
     y: Tensor = None                # raw conv output (N,D',H',W',Cout)
-    coef: Tensor = None             # (N,Cout,2) fp32  A,B
-    mr: Tensor = None               # (N,G,2)   fp32  mean, rstd
+    coef: Tensor = None             # (N,Cout,2) fp32  A,B          (unfused path only)
+    mr: Tensor = None               # (N,G,2)   fp32  mean, rstd    (unfused path only)
+    gn: tuple = None                # (stats, gamma, beta, scale, vox, groups, eps): fused-coefficient path
     scale: Optional[Tensor] = None  # (N,Cout) dropout scale or None
 
 
@@ -158,13 +159,17 @@ class Engine:
         stats = self.zeros((n, cout, 2), torch.float64, x.device)
         self.conv_raw(kind, wname, bname, x, L.y, stats)
         L.scale = self._next_mask()
-        L.coef = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
-        L.mr = torch.empty((n, GROUPS, 2), dtype=torch.float32, device=x.device)
         vox = 1
         for s in out_sp:
             vox *= s
-        self.be.gn_finalize(stats, self.P[gname + ".weight"], self.P[gname + ".bias"], L.scale, vox,
-                            GROUPS, GN_EPS, L.coef, L.mr)
+        if getattr(self.be, "fused_gn", False):
+            # kernels derive the coefficients from the statistics themselves: no finalize launch
+            L.gn = (stats, self.P[gname + ".weight"], self.P[gname + ".bias"], L.scale, vox, GROUPS, GN_EPS)
+        else:
+            L.coef = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
+            L.mr = torch.empty((n, GROUPS, 2), dtype=torch.float32, device=x.device)
+            self.be.gn_finalize(stats, self.P[gname + ".weight"], self.P[gname + ".bias"], L.scale, vox,
+                                GROUPS, GN_EPS, L.coef, L.mr)
         self.layers.append(L)
         return L
 
@@ -185,7 +190,10 @@ class Engine:
         return self.bwd_layer(Lh, g_logits, True, dx_out=dx)
 
     def act(self, L: Layer, out: Tensor, L2: Optional[Layer] = None, res: Optional[Tensor] = None) -> Tensor:
-        self.be.apply(L.y, L.coef, L2.y if L2 is not None else None, L2.coef if L2 is not None else None, res, out)
+        if L.gn is not None:
+            self.be.apply_gn(L.y, L.gn, L2.y if L2 is not None else None, L2.gn if L2 is not None else None, res, out)
+        else:
+            self.be.apply(L.y, L.coef, L2.y if L2 is not None else None, L2.coef if L2 is not None else None, res, out)
         return out
 
     # ---------------------------------------------------------------- backward primitives
@@ -201,7 +209,14 @@ class Engine:
         n, cout = L.y.shape[0], L.y.shape[-1]
         dev = L.y.device
         vox = L.y.numel() // (n * cout)
-        if L.gname is not None:
+        if L.gname is not None and L.gn is not None:
+            sums = self.zeros((n, cout, 3), torch.float64, dev)
+            be.gn_bwd_reduce_gn(g_act, L.y, L.gn, sums)
+            dy = torch.empty(L.y.shape, dtype=self.T, device=dev)
+            be.gn_bwd_apply_gn(g_act, L.y, L.gn, sums, dy, self._grad_view(L.gname + ".weight"),
+                               self._grad_view(L.gname + ".bias"),
+                               self._grad_view(L.bname) if L.bname is not None else None)
+        elif L.gname is not None:
             sums = self.zeros((n, cout, 3), torch.float64, dev)
             be.gn_bwd_reduce(g_act, L.y, L.coef, sums)
             coef3 = torch.empty((n, cout, 3), dtype=torch.float32, device=dev)

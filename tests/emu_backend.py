@@ -130,6 +130,33 @@ class EmuBackend:
         coef[..., 0] = (r_c * g64 * s).float()
         coef[..., 1] = ((b64 - mu_c * r_c * g64) * s).float()
 
+    # fused-coefficient forms (composition of the unfused statements above)
+    fused_gn = True
+
+    def _coef(self, gn, n, c):
+        stats, gamma, beta, scale, vox, groups, eps = gn
+        coef, mr = torch.empty(n, c, 2), torch.empty(n, groups, 2)
+        self.gn_finalize(stats, gamma, beta, scale, vox, groups, eps, coef, mr)
+        return coef, mr
+
+    def apply_gn(self, y1, gn1, y2, gn2, res, out):
+        n, c = y1.shape[0], y1.shape[-1]
+        c1, _ = self._coef(gn1, n, c)
+        c2 = self._coef(gn2, n, c)[0] if y2 is not None else None
+        self.apply(y1, c1, y2, c2, res, out)
+
+    def gn_bwd_reduce_gn(self, g, y, gn, sums):
+        coef, _ = self._coef(gn, y.shape[0], y.shape[-1])
+        self.gn_bwd_reduce(g, y, coef, sums)
+
+    def gn_bwd_apply_gn(self, g, y, gn, sums, dy, dgamma, dbeta, dbias):
+        n, c = y.shape[0], y.shape[-1]
+        stats, gamma, beta, scale, vox, groups, eps = gn
+        coef, mr = self._coef(gn, n, c)
+        coef3 = torch.empty(n, c, 3)
+        self.gn_bwd_finalize(sums, mr, gamma, scale, vox, groups, coef3, dgamma, dbeta, dbias)
+        self.gn_bwd_apply(g, y, coef, coef3, dy)
+
     def apply(self, y1, c1, y2, c2, res, out):
         def one(y, c):
             a = c[..., 0].view(c.shape[0], 1, 1, 1, -1)

@@ -298,3 +298,47 @@ def test_fused_head(be, dtype, nc, cin):
     if ok:
         assert rel(dx_c, dx_e) < tol(dtype, 0.5)
         assert rel(dw_c, dw_e) < 1e-5 and rel(db_c, db_e) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,sp,c,masked", [(2, (4, 6, 8), 16, True), (1, (3, 5, 7), 32, False),
+                                           (2, (1, 8, 8), 64, True), (1, (2, 2, 2), 256, True)])
+def test_groupnorm_fused_coefficient_forms(be, dtype, n, sp, c, masked):
+    """apply_gn / gn_bwd_reduce_gn / gn_bwd_apply_gn (coefficients derived in-kernel from the statistics)
+    against the composition of the unfused statements."""
+    g = torch.Generator().manual_seed(31)
+    y = sliced(n, sp, c, dtype, g, pad=16)
+    y2 = rnd((n,) + sp + (c,), dtype, g)
+    res = rnd((n,) + sp + (c,), dtype, g)
+    gamma = 1 + 0.2 * torch.randn(c, generator=g)
+    beta = 0.2 * torch.randn(c, generator=g)
+    scale = (torch.rand(n, c, generator=g) > 0.2).float() / 0.8 if masked else None
+    vox = sp[0] * sp[1] * sp[2]
+
+    def stats_of(t):
+        tf = t.double()
+        return torch.stack([tf.sum((1, 2, 3)), (tf * tf).sum((1, 2, 3))], -1).contiguous()
+
+    gn1 = (stats_of(y), gamma, beta, scale, vox, 8, 1e-5)
+    gn2 = (stats_of(y2), gamma, beta, None, vox, 8, 1e-5)
+    cu = lambda gn: tuple(v.cuda() if isinstance(v, torch.Tensor) else v for v in gn)
+    out_e = torch.empty((n,) + sp + (c,), dtype=dtype)
+    EMU.apply_gn(y, gn1, y2, gn2, res, out_e)
+    out_c = torch.empty((n,) + sp + (c,), dtype=dtype, device="cuda")
+    be.apply_gn(y.cuda(), cu(gn1), y2.cuda(), cu(gn2), res.cuda(), out_c)
+    assert rel(out_c, out_e) < tol(dtype, 0.5)
+    gact = rnd((n,) + sp + (c,), dtype, g)
+    sums_e = torch.zeros(n, c, 3, dtype=torch.float64)
+    EMU.gn_bwd_reduce_gn(gact, y, gn1, sums_e)
+    sums_c = torch.zeros(n, c, 3, dtype=torch.float64, device="cuda")
+    be.gn_bwd_reduce_gn(gact.cuda(), y.cuda(), cu(gn1), sums_c)
+    assert rel(sums_c, sums_e) < 1e-5
+    dy_e = torch.empty((n,) + sp + (c,), dtype=dtype)
+    dg_e, db_e, dbi_e = torch.ones(c), torch.ones(c), torch.zeros(c)
+    EMU.gn_bwd_apply_gn(gact, y, gn1, sums_e, dy_e, dg_e, db_e, dbi_e)
+    dy_c = torch.empty((n,) + sp + (c,), dtype=dtype, device="cuda")
+    dg_c, db_c, dbi_c = torch.ones(c, device="cuda"), torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    be.gn_bwd_apply_gn(gact.cuda(), y.cuda(), cu(gn1), sums_e.cuda(), dy_c, dg_c, db_c, dbi_c)
+    assert rel(dy_c, dy_e) < tol(dtype, 0.5)
+    assert rel(dg_c, dg_e) < 1e-5 and rel(db_c, db_e) < 1e-5
+    assert (dbi_c.cpu() - dbi_e).abs().max() < 1e-4 * (1 + dbi_e.abs().max())
