@@ -41,6 +41,63 @@ NUMCLASS = 2
 # algorithmic work of one fwd+bwd step of VNet3d(1,2) 96^3 B=2 (bf16 storage)
 STEP_GFLOP = 433.11
 STEP_MB = 3239.9
+ARCH = "vnet3d"
+LOSS = "MutilDiceLoss"
+
+# --workload: the headline metric is vnet3d96 (BASELINE.json configs[1]/[3]); the others are the remaining
+# GPU configs of BASELINE.json, timed with the same harness for DESIGN.md (not the graded bench line)
+WORKLOADS = {
+    "vnet3d96": dict(arch="vnet3d", spatial=(96, 96, 96), batch=2, ncls=2, loss="MutilDiceLoss", gflop=433.11,
+                     mb=3239.9, desc="VNet3d(1,2) 96x96x96, batch 2 per GPU"),
+    "unet3d128": dict(arch="unet3d", spatial=(128, 128, 128), batch=1, ncls=4, loss="MutilCrossEntropyDiceLoss",
+                      gflop=715.01, mb=3393.9, desc="UNet3d(1,4) 128x128x128, batch 1 per GPU"),
+    "unet2d512": dict(arch="unet2d", spatial=(512, 512), batch=8, ncls=1, loss="BinaryDiceFocalLoss", gflop=578.01,
+                      mb=4841.1, desc="UNet2d(1,1) 512x512, batch 8 per GPU"),
+}
+
+
+def select_workload(name):
+    global SPATIAL, BATCH_PER_GPU, NUMCLASS, STEP_GFLOP, STEP_MB, ARCH, LOSS, WL_DESC
+    w = WORKLOADS[name]
+    SPATIAL, BATCH_PER_GPU, NUMCLASS = w["spatial"], w["batch"], w["ncls"]
+    STEP_GFLOP, STEP_MB, ARCH, LOSS, WL_DESC = w["gflop"], w["mb"], w["arch"], w["loss"], w["desc"]
+
+
+WL_DESC = WORKLOADS["vnet3d96"]["desc"]
+
+
+def voxels_per_sample():
+    v = 1
+    for s_ in SPATIAL:
+        v *= s_
+    return v
+
+
+def oracle_step_fn():
+    """(state_dict with grads, step()) for the CPU arm of the selected workload."""
+    import oracle
+    from oracle import nets as onets
+    if ARCH == "vnet3d":
+        spec = onets.vnet3d_state_spec(1, NUMCLASS)
+        fwd = lambda sd, x, m: onets.vnet3d_forward(sd, x, m)
+        draw = lambda n: onets.draw_dropout_masks_vnet3d(n)
+    else:
+        dims = 3 if ARCH == "unet3d" else 2
+        spec = onets.unet_state_spec(1, NUMCLASS, dims)
+        fwd = lambda sd, x, m: onets.unet_forward(sd, x, dims, m)
+        draw = lambda n: onets.draw_dropout_masks_unet(n, dims)
+    sd = {k: v.requires_grad_(True) for k, v in onets.init_state_dict(spec, seed=0).items()}
+    x, y = make_batch(0, 1)
+    alpha = torch.ones(NUMCLASS)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        logits, _ = fwd(sd, x, draw(x.shape[0]))
+        loss = oracle.loss_forward(LOSS, logits, y, alpha)
+        loss.backward()
+        return float(loss.detach())
+    return step
 
 
 def load_peaks():
@@ -193,19 +250,7 @@ def run_reference(args):
         return
     cores = pick_cpu_threads()
     torch.set_num_threads(cores)
-    spec = onets.vnet3d_state_spec(1, NUMCLASS)
-    sd = {k: v.requires_grad_(True) for k, v in onets.init_state_dict(spec, seed=0).items()}
-    x, y = make_batch(0, 1)
-    alpha = torch.ones(NUMCLASS)
-
-    def step():
-        for v in sd.values():
-            v.grad = None
-        masks = onets.draw_dropout_masks_vnet3d(x.shape[0])
-        logits, _ = onets.vnet3d_forward(sd, x, masks)
-        loss = oracle.loss_forward("MutilDiceLoss", logits, y, alpha)
-        loss.backward()
-        return float(loss)
+    step = oracle_step_fn()
 
     steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
     for _ in range(warm):
@@ -216,15 +261,15 @@ def run_reference(args):
         step()
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
-    vox = BATCH_PER_GPU * SPATIAL[0] * SPATIAL[1] * SPATIAL[2]
+    vox = BATCH_PER_GPU * voxels_per_sample()
     val = vox / t
     line = {"impl": "reference", "metric": "voxels_per_sec_fwd_bwd", "value": val, "unit": "voxels/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VNet3d(1,2) 96x96x96 batch 2, fwd+loss(MutilDice)+bwd, train mode, CPU fp32",
+            "config": {"workload": WL_DESC + ", fwd+loss(" + LOSS + ")+bwd, train mode, CPU fp32",
                        "global_batch": BATCH_PER_GPU},
             "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{steps} full steps (2x96^3 voxels each) of the oracle restatement on "
+                             "sample": f"{steps} full steps ({WL_DESC}) of the oracle restatement on "
                                        f"{torch.get_num_threads()} host threads"},
             "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -259,26 +304,18 @@ def cpu_baseline_sample():
     prev = torch.get_num_threads()
     cores = pick_cpu_threads()
     torch.set_num_threads(cores)
-    spec = onets.vnet3d_state_spec(1, NUMCLASS)
-    sd = {k: v.requires_grad_(True) for k, v in onets.init_state_dict(spec, seed=0).items()}
-    x, y = make_batch(0, 1)
-    alpha = torch.ones(NUMCLASS)
+    step = oracle_step_fn()
     ts = []
     for i in range(3):
-        for v in sd.values():
-            v.grad = None
         t0 = time.perf_counter()
-        masks = onets.draw_dropout_masks_vnet3d(x.shape[0])
-        logits, _ = onets.vnet3d_forward(sd, x, masks)
-        loss = oracle.loss_forward("MutilDiceLoss", logits, y, alpha)
-        loss.backward()
+        step()
         if i > 0:
             ts.append(time.perf_counter() - t0)
     torch.set_num_threads(prev)
     t = statistics.median(ts)
-    vox = BATCH_PER_GPU * SPATIAL[0] * SPATIAL[1] * SPATIAL[2]
+    vox = BATCH_PER_GPU * voxels_per_sample()
     return {"value": vox / t, "unit": "voxels/s", "cores": cores, "kind": "port",
-            "sample": f"2 timed full steps (+1 warm-up) of VNet3d 96^3 B=2 fwd+loss+bwd, oracle restatement, fp32, "
+            "sample": f"2 timed full steps (+1 warm-up) of {WL_DESC} fwd+loss+bwd, oracle restatement, fp32, "
                       f"{cores} host threads; median {t * 1e3:.0f} ms/step"}
 
 
@@ -291,7 +328,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="vnet3d96", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     args.warmup = max(3, args.warmup)
 
     if args.impl == "reference":
@@ -317,10 +356,11 @@ def main():
     b200.set_precision(args.precision)
 
     torch.manual_seed(0)
-    model = b200.VNet3d(1, NUMCLASS)
+    model = {"vnet3d": b200.VNet3d, "unet3d": b200.UNet3d, "unet2d": b200.UNet2d}[ARCH](1, NUMCLASS)
     model.apply(b200.initialize_weights)
     model = model.to(dev).train()
-    lossfn = b200.MutilDiceLoss(torch.ones(NUMCLASS, device=dev))
+    losscls = getattr(b200, LOSS)
+    lossfn = losscls(torch.ones(NUMCLASS, device=dev)) if LOSS.startswith("Mutil") else losscls()
     xh, yh = make_batch(rank, world)
     xh, yh = xh.pin_memory(), yh.pin_memory()
     x, y = xh.to(dev), yh.to(dev)
@@ -415,7 +455,7 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     t_step = tot[0].item() / args.steps * 1e-3
     t_e2e = tot[1].item() / args.steps * 1e-3
-    vox_step = world * BATCH_PER_GPU * SPATIAL[0] * SPATIAL[1] * SPATIAL[2]
+    vox_step = world * BATCH_PER_GPU * voxels_per_sample()
 
     if rank == 0:
         peaks = load_peaks()
@@ -445,8 +485,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": "VNet3d(1,2) 96x96x96, batch 2 per GPU, fwd (train mode, dropout masks drawn) + "
-                                   "MutilDiceLoss + bwd of all 128 parameter tensors"
+            "config": {"workload": WL_DESC + ", fwd (train mode, dropout masks drawn) + " + LOSS +
+                                   " + bwd of all parameter tensors"
                                    + (" + NCCL SUM all-reduce of the flat fp32 gradient bucket" if world > 1 else ""),
                        "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
                        "l2": "256 MiB flush before every timed step; per-step working set > 1 GB >> 126 MB L2",

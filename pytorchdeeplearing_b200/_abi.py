@@ -313,7 +313,7 @@ class CudaBackend:
         self._check(self.lib.b200seg_apply(C.byref(d1), c1.data_ptr(), _ref(d2), _p(c2), _ref(dr), C.byref(do), dev, st))
 
     # fused-coefficient forms: gn = (stats, gamma, beta, scale|None, vox, groups, eps)
-    fused_gn = True
+    fused_gn = os.environ.get("B200SEG_FUSED_GN", "1") != "0"
 
     @staticmethod
     def _gn(gn):

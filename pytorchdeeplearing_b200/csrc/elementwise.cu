@@ -262,20 +262,33 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
   EW_PROLOGUE(C)
   float A1[VEC], B1[VEC], A2[VEC], B2[VEC];
   if (gn1.stats != nullptr) {
-    gn_coef_from_stats<VEC>(gn1, n, C, c0, A1, B1, nullptr, nullptr);
+    // coefficients once per CTA (one thread per channel), then broadcast through shared memory
+    extern __shared__ float s_cf[];                       // [4][C]: A1, B1, A2, B2
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a_, b_;
+      gn_coef_from_stats<1>(gn1, n, C, c, &a_, &b_, nullptr, nullptr);
+      s_cf[c] = a_;
+      s_cf[C + c] = b_;
+      if (y2 != nullptr) {
+        gn_coef_from_stats<1>(gn2, n, C, c, &a_, &b_, nullptr, nullptr);
+        s_cf[2 * C + c] = a_;
+        s_cf[3 * C + c] = b_;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      A1[j] = s_cf[c0 + j];
+      B1[j] = s_cf[C + c0 + j];
+      A2[j] = y2 != nullptr ? s_cf[2 * C + c0 + j] : 0.f;
+      B2[j] = y2 != nullptr ? s_cf[3 * C + c0 + j] : 0.f;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float* p = coef1 + ((long long)n * C + c0 + j) * 2;
       A1[j] = p[0];
       B1[j] = p[1];
-    }
-  }
-  if (y2 != nullptr && gn2.stats != nullptr) {
-    gn_coef_from_stats<VEC>(gn2, n, C, c0, A2, B2, nullptr, nullptr);
-  } else {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
       if (y2 != nullptr) {
         const float* q = coef2 + ((long long)n * C + c0 + j) * 2;
         A2[j] = q[0];
@@ -323,7 +336,21 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   __syncthreads();
   float A[VEC], B[VEC];
   float f1[VEC], f2[VEC], f3[VEC];
-  if (gn.stats != nullptr) gn_coef_from_stats<VEC>(gn, n, C, c0, A, B, nullptr, nullptr);
+  if (gn.stats != nullptr) {
+    float* s_ab = reinterpret_cast<float*>(s_redd + 3 * C);      // [2][C] after the fp64 scratch
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a_, b_;
+      gn_coef_from_stats<1>(gn, n, C, c, &a_, &b_, nullptr, nullptr);
+      s_ab[c] = a_;
+      s_ab[C + c] = b_;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      A[j] = s_ab[c0 + j];
+      B[j] = s_ab[C + c0 + j];
+    }
+  }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     if (gn.stats == nullptr) {
@@ -441,11 +468,29 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
   EW_PROLOGUE(C)
   float A[VEC], B[VEC], P[VEC], Q[VEC], R[VEC];
   if (gn.stats != nullptr) {
-    double MU[VEC], RS[VEC];
-    gn_coef_from_stats<VEC>(gn, n, C, c0, A, B, MU, RS);
-    gn_bwd_coef_from_sums<VEC>(gn, sums, n, C, c0, MU, RS, P, Q, R);
-    // parameter gradients (d gamma, d beta, d bias): one block, fixed order over the samples
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
+    extern __shared__ float s_c5[];                       // [5][C]: A, B, P, Q, R of sample n
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a_, b_, p_, q_, r_;
+      double mu_, rs_;
+      gn_coef_from_stats<1>(gn, n, C, c, &a_, &b_, &mu_, &rs_);
+      gn_bwd_coef_from_sums<1>(gn, sums, n, C, c, &mu_, &rs_, &p_, &q_, &r_);
+      s_c5[c] = a_;
+      s_c5[C + c] = b_;
+      s_c5[2 * C + c] = p_;
+      s_c5[3 * C + c] = q_;
+      s_c5[4 * C + c] = r_;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      A[j] = s_c5[c0 + j];
+      B[j] = s_c5[C + c0 + j];
+      P[j] = s_c5[2 * C + c0 + j];
+      Q[j] = s_c5[3 * C + c0 + j];
+      R[j] = s_c5[4 * C + c0 + j];
+    }
+    // parameter gradients (d gamma, d beta, d bias): the LAST block of the grid, fixed order over the samples
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) {
       const int cpg = C / gn.groups;
       const double vox = gn.m / (double)cpg;
       for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -732,7 +777,7 @@ int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, co
   EW_DISPATCH(out, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, out->n, device), out->n);
-    apply_kernel<T, VEC><<<grid, 256, 0, s>>>(
+    apply_kernel<T, VEC><<<grid, 256, 4 * C * sizeof(float), s>>>(
         static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
         res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V,
         make_gnref(g1, C), make_gnref(g2, C));
@@ -750,7 +795,7 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
-    gn_bwd_reduce_kernel<T, VEC><<<grid, 256, 3 * C * sizeof(double), s>>>(
+    gn_bwd_reduce_kernel<T, VEC><<<grid, 256, 3 * C * sizeof(double) + 2 * C * sizeof(float), s>>>(
         static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
         make_gnref(gn, C));
   });
@@ -780,7 +825,7 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
-    gn_bwd_apply_kernel<T, VEC><<<grid, 256, 0, s>>>(static_cast<const T*>(g->ptr), g->ld,
+    gn_bwd_apply_kernel<T, VEC><<<grid, 256, 5 * C * sizeof(float), s>>>(static_cast<const T*>(g->ptr), g->ld,
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
                                                      static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
                                                      y->n, dgamma, dbeta, dbias);
