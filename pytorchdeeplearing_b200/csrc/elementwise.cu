@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
                                                             const T* __restrict__ y, long long ldy,
                                                             const float* __restrict__ coef,
                                                             double* __restrict__ sums, int C, long long V,
-                                                            const GnRef gn) {
+                                                            const GnRef gn, const int staged) {
   EW_PROLOGUE(C)
   extern __shared__ double s_redd[];   // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_redd[i] = 0.0;
@@ -395,7 +395,28 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
       }
     }
   }
-  if ((int)(threadIdx.x & 31) < lane_groups) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (staged) {
+    // every warp covers all C channels with its first G lanes: private rows, no atomics, fixed summation order
+    double* s_part = s_redd + 3 * C + (C + 1) / 2 * 2;      // [8 warps][3][C], after scratch + coefficient floats
+    if (lane < lane_groups) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        s_part[(wid * 3 + 0) * C + c0 + j] = s1[j];
+        s_part[(wid * 3 + 1) * C + c0 + j] = s2[j];
+        s_part[(wid * 3 + 2) * C + c0 + j] = s3[j];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+      const int k = i / C, c = i - k * C;
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[(w * 3 + k) * C + c];
+      atomicAdd(sums + ((long long)n * C + c) * 3 + k, t);
+    }
+    return;
+  }
+  if (lane < lane_groups) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       atomicAdd(&s_redd[0 * C + c0 + j], s1[j]);
@@ -795,9 +816,13 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
-    gn_bwd_reduce_kernel<T, VEC><<<grid, 256, 3 * C * sizeof(double) + 2 * C * sizeof(float), s>>>(
+    const bool pow2g = (G & (G - 1)) == 0;
+    const size_t base = 3 * C * sizeof(double) + (size_t)((C + 1) / 2 * 2) * sizeof(double);
+    const size_t staged_bytes = base + (size_t)8 * 3 * C * sizeof(double);
+    const int staged = (pow2g && G <= 32 && staged_bytes <= 44 * 1024) ? 1 : 0;
+    gn_bwd_reduce_kernel<T, VEC><<<grid, 256, staged ? staged_bytes : base, s>>>(
         static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
-        make_gnref(gn, C));
+        make_gnref(gn, C), staged);
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;

@@ -103,100 +103,64 @@ __global__ void __launch_bounds__(256) conv_smallcin_kernel(const TX* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem weight gradient.  CTA tile = 128 consecutive output voxels (linear n,d,h,w order; the stem input is a
-// dense NDHWC tensor with ld == Cin).  Per tile the kd input d-slices needed by all taps are staged in smem
-// as linear ranges [v0 + (kd-pd)*H*W - (W+1), +128 + 2W + 2), the 128 dy rows as fp32, and a per-voxel
-// bit mask says which taps fall inside the volume.  Thread <-> (half of the tile, row r = (tap, ci),
-// 4 output channels): every inner-loop operand comes from shared memory.
+// stem weight gradient.  dwp[t][ci][co] += sum_v x[v+t][ci] * dy[v][co]  with Cin <= 4.
+// Lane <-> role r = (tap, ci); one voxel per group of ceil(R/32) warps at a time: all lanes of a warp read the
+// SAME dy row (one broadcast transaction of COUT channels) and each its own shifted x element, so every
+// thread keeps COUT accumulators for its (tap, ci) pair; nothing is staged, the reads stream through L1.
 // ------------------------------------------------------------------------------------------------
 template <typename TA, typename TB, int COUT>
-__global__ void __launch_bounds__(256) wgrad_smallcin_kernel(const TA* __restrict__ a, const TB* __restrict__ b,
-                                                             long long bld, float* __restrict__ dwp, int N, int D,
-                                                             int H, int W, int Cin, int kd, int kh, int kw, int pd,
-                                                             int ph, int pw, int chunk) {
-  constexpr int TILE = 128;
-  constexpr int Q = COUT / 4;
-  extern __shared__ __align__(16) float s_dyn[];
-  const int span = TILE + 2 * W + 2;                // staged voxels per d-slice
-  float* s_dy = s_dyn;                              // [TILE][COUT]
-  float* s_x = s_dy + TILE * COUT;                  // [kd][span][Cin]
-  unsigned* s_mask = reinterpret_cast<unsigned*>(s_x + (size_t)kd * span * Cin);   // [TILE]
+__global__ void __launch_bounds__(256) wgrad_smallcin_kernel(const TA* __restrict__ a, long long ald,
+                                                             const TB* __restrict__ b, long long bld,
+                                                             float* __restrict__ dwp, int N, int D, int H, int W,
+                                                             int Cin, int kd, int kh, int kw, int pd, int ph, int pw) {
+  __shared__ float s_red[8][32][COUT + 1];
   const int taps = kd * kh * kw;
   const int R = taps * Cin;
+  const int wpv = (R + 31) / 32;                  // warps cooperating on one voxel
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int vslot = wid / wpv;                    // voxel slot of this warp inside the block
+  const int slots = 8 / wpv;                      // voxels processed per block iteration
+  const int r = (wid % wpv) * 32 + lane;          // role
+  const bool active = r < R && vslot < slots;
+  const int tap = active ? r / Cin : 0, ci = active ? r - tap * Cin : 0;
+  const int cw = tap % kw - pw, ch_ = (tap / kw) % kh - ph, cd = tap / (kw * kh) - pd;
   const long long V = (long long)D * H * W;
   const long long NV = (long long)N * V;
-  const int half = threadIdx.x >> 7;                // 0 / 1: which 64 voxels of the tile
-  const int ht = threadIdx.x & 127;
-  const int slots = 128 / Q;
-  const int q = ht % Q;
-  const int slot = ht / Q;
-  const long long v_begin = (long long)blockIdx.x * chunk;
-  long long v_end = v_begin + chunk;
-  if (v_end > NV) v_end = NV;
-  float acc[4][4];
+  float acc[COUT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  if (vslot < slots) {
+    for (long long gv = (long long)blockIdx.x * slots + vslot; gv < NV; gv += (long long)gridDim.x * slots) {
+      const int n = (int)(gv / V);
+      const long long o = gv - (long long)n * V;
+      const int ow = (int)(o % W), oh = (int)((o / W) % H), od = (int)(o / ((long long)W * H));
+      const int id = od + cd, ih = oh + ch_, iw = ow + cw;
+      float xv = 0.f;
+      if (active && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+        xv = to_f(a[((((long long)n * D + id) * H + ih) * W + iw) * ald + ci]);
+      const TB* pb = b + gv * bld;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long v0 = v_begin; v0 < v_end; v0 += TILE) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < TILE * Q; i += blockDim.x) {
-      const int lv = i / Q, lq = i % Q;
-      const long long gv = v0 + lv;
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gv < v_end) val = load4(b + gv * bld + 4 * lq);
-      *reinterpret_cast<float4*>(&s_dy[lv * COUT + 4 * lq]) = val;
-    }
-    for (int k = 0; k < kd; ++k) {
-      const long long base = v0 + (long long)(k - pd) * H * W - (W + 1);
-      for (int i = threadIdx.x; i < span * Cin; i += blockDim.x) {
-        const long long e = base * Cin + i;
-        s_x[(size_t)k * span * Cin + i] = (e >= 0 && e < NV * Cin) ? to_f(a[e]) : 0.f;
-      }
-    }
-    for (int lv = threadIdx.x; lv < TILE; lv += blockDim.x) {
-      const long long gv = v0 + lv;
-      unsigned m = 0;
-      if (gv < v_end) {
-        const long long o = gv % V;
-        const int ow = (int)(o % W), oh = (int)((o / W) % H), od = (int)(o / ((long long)W * H));
-        int tap = 0;
-        for (int cd = 0; cd < kd; ++cd)
-          for (int ch_ = 0; ch_ < kh; ++ch_)
-            for (int cw = 0; cw < kw; ++cw, ++tap) {
-              const int id = od + cd - pd, ih = oh + ch_ - ph, iw = ow + cw - pw;
-              if ((unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) m |= 1u << tap;
-            }
-      }
-      s_mask[lv] = m;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = slot + i * slots;
-      if (r >= R) break;
-      const int tap = r / Cin, ci = r - tap * Cin;
-      const int cw = tap % kw, ch_ = (tap / kw) % kh, cd = tap / (kw * kh);
-      // x for output voxel lv and this tap sits at slice cd, offset lv + (ch-ph+1)*W + (cw-pw+1) (K3: ch*W + cw)
-      const float* xs = s_x + (size_t)cd * span * Cin + (size_t)((ch_ - ph + 1) * W + (cw - pw + 1)) * Cin + ci;
-      const int lv0 = half * (TILE / 2);
-#pragma unroll 4
-      for (int lv = lv0; lv < lv0 + TILE / 2; ++lv) {
-        const float xv = ((s_mask[lv] >> tap) & 1u) ? xs[(size_t)lv * Cin] : 0.f;
-        const float4 dv = *reinterpret_cast<const float4*>(&s_dy[lv * COUT + 4 * q]);
-        acc[i][0] = fmaf(xv, dv.x, acc[i][0]);
-        acc[i][1] = fmaf(xv, dv.y, acc[i][1]);
-        acc[i][2] = fmaf(xv, dv.z, acc[i][2]);
-        acc[i][3] = fmaf(xv, dv.w, acc[i][3]);
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 dv = load4(pb + 4 * c4);
+        acc[4 * c4 + 0] = fmaf(xv, dv.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(xv, dv.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(xv, dv.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(xv, dv.w, acc[4 * c4 + 3]);
       }
     }
   }
+  // fold the voxel slots: role r of every slot -> one atomic per (role, channel) per block
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = slot + i * slots;
-    if (r >= R) break;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dwp + (long long)r * COUT + 4 * q + j, acc[i][j]);
+  for (int c = 0; c < COUT; ++c) s_red[wid][lane][c] = active ? acc[c] : 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < wpv * 32 * COUT; i += blockDim.x) {
+    const int c = i % COUT;
+    const int rr = i / COUT;                      // role
+    if (rr >= R) continue;
+    const int w_in = rr / 32, l = rr % 32;
+    float t = 0.f;
+    for (int sl = 0; sl < slots; ++sl) t += s_red[sl * wpv + w_in][l][c];
+    atomicAdd(dwp + (long long)rr * COUT + c, t);
   }
 }
 
@@ -373,9 +337,7 @@ int smallcin_conv(int kind, int dims, const b200seg_tensor* x, const void* w, in
 
 int smallcin_wgrad_supported(int kind, const b200seg_tensor* a, const b200seg_tensor* b) {
   if (kind != B200SEG_K3 && kind != B200SEG_K1) return 0;
-  if (a->c > 4 || a->ld != a->c) return 0;                       // dense stem input (linear staging)
-  if ((long long)(128 + 2 * a->w + 2) * a->c * 3 * 4 > 96 * 1024) return 0;
-  if ((kind == B200SEG_K3 ? 27 : 1) * a->c > 2048 / (b->c > 0 ? b->c : 1)) return 0;   // rows per thread <= 4
+  if (a->c > 4) return 0;
   if (b->c != 8 && b->c != 16 && b->c != 24 && b->c != 32) return 0;
   if ((b->ld % 4) || !al16s(b->ptr)) return 0;
   if (b->dtype == B200SEG_BF16 && (b->ld % 8)) return 0;
@@ -387,25 +349,12 @@ template <typename TA, typename TB>
 static int smallcin_wgrad_typed(const ConvGeom& g, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp,
                                 int device, cudaStream_t st) {
   const long long NV = (long long)b->n * b->d * b->h * b->w;
-  long long ctas = (long long)num_sms(device) * 16;   // many small CTAs: the per-tile staging latency overlaps across CTAs
-  long long chunk = (NV + ctas - 1) / ctas;
-  chunk = ((chunk + 127) / 128) * 128;
-  if (chunk < 128) chunk = 128;
-  const long long grid = (NV + chunk - 1) / chunk;
-  const size_t smem = ((size_t)128 * b->c + (size_t)g.kd * (128 + 2 * b->w + 2) * a->c + 128) * sizeof(float);
-  if (smem > 48 * 1024) {
-    static bool optin_done[4] = {false, false, false, false};
-    (void)optin_done;
-  }
+  long long grid = (long long)num_sms(device) * 8;
+  if (grid > NV) grid = NV;
 #define LAUNCH_SW(CO)                                                                                        \
-  do {                                                                                                       \
-    if (smem > 48 * 1024)                                                                                    \
-      cudaFuncSetAttribute(wgrad_smallcin_kernel<TA, TB, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                           (int)smem);                                                                       \
-    wgrad_smallcin_kernel<TA, TB, CO><<<(unsigned)grid, 256, smem, st>>>(                                    \
-        static_cast<const TA*>(a->ptr), static_cast<const TB*>(b->ptr), b->ld, dwp, b->n, b->d, b->h, b->w,  \
-        a->c, g.kd, g.kh, g.kw, g.pd, g.ph, g.pw, (int)chunk);                                               \
-  } while (0)
+  wgrad_smallcin_kernel<TA, TB, CO><<<(unsigned)grid, 256, 0, st>>>(                                         \
+      static_cast<const TA*>(a->ptr), a->ld, static_cast<const TB*>(b->ptr), b->ld, dwp, b->n, b->d, b->h,   \
+      b->w, a->c, g.kd, g.kh, g.kw, g.pd, g.ph, g.pw)
   switch (b->c) {
     case 8: LAUNCH_SW(8); break;
     case 16: LAUNCH_SW(16); break;
