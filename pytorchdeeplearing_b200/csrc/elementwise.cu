@@ -250,7 +250,10 @@ template <typename T> struct Vec<T, 1> {
   const long long stride = (long long)gridDim.x * blockDim.x;                    \
   long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x;               \
   const int cg = (int)(gi % G);                                                  \
-  const int c0 = cg * VEC;
+  const int c0 = cg * VEC;                                                       \
+  long long vi = gi / G;            /* voxel of the first group of this thread */ \
+  const long long vstep = stride / G; /* stride is a multiple of G */          \
+  (void)total;
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, long long ld1,
@@ -299,8 +302,8 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
       }
     }
   }
-  for (; gi < total; gi += stride) {
-    long long vox = (long long)n * V + gi / G;
+  for (; vi < V; vi += vstep) {
+    const long long vox = (long long)n * V + vi;
     float a[VEC], o[VEC];
     Vec<T, VEC>::load(y1 + vox * ld1 + c0, a);
 #pragma unroll
@@ -362,8 +365,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   }
   // a thread sees only ~10 voxel groups (grid sized to the chip): its partial sums stay in fp32, everything
   // after that (cross-lane, cross-warp, cross-CTA) is accumulated in fp64
-  for (; gi < total; gi += stride) {
-    const long long vox = (long long)n * V + gi / G;
+  for (; vi < V; vi += vstep) {
+    const long long vox = (long long)n * V + vi;
     float yv[VEC], gv[VEC];
     Vec<T, VEC>::load(y + vox * ldy + c0, yv);
     Vec<T, VEC>::load(g + vox * ldg + c0, gv);
@@ -545,8 +548,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
       R[j] = q[2];
     }
   }
-  for (; gi < total; gi += stride) {
-    long long vox = (long long)n * V + gi / G;
+  for (; vi < V; vi += vstep) {
+    const long long vox = (long long)n * V + vi;
     float yv[VEC], gv[VEC], o[VEC];
     Vec<T, VEC>::load(y + vox * ldy + c0, yv);
     Vec<T, VEC>::load(g + vox * ldg + c0, gv);
@@ -570,8 +573,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
   float s[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) s[j] = 0.f;
-  for (; gi < total; gi += stride) {
-    long long vox = (long long)n * V + gi / G;
+  for (; vi < V; vi += vstep) {
+    const long long vox = (long long)n * V + vi;
     float v[VEC];
     Vec<T, VEC>::load(x + vox * ld + c0, v);
 #pragma unroll

@@ -37,10 +37,11 @@ __global__ void __launch_bounds__(256) conv_smallcin_kernel(const TX* __restrict
 #pragma unroll
   for (int c = 0; c < COUT; ++c) ssum[c] = ssq[c] = 0.f;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
-    const int ow = (int)(v % W);
-    const long long t2 = v / W;
-    const int oh = (int)(t2 % H);
-    const int od = (int)(t2 / H);
+    const int vi = (int)v;                 // voxels per sample < 2^31: 32-bit decode
+    const int ow = vi % W;
+    const int t2 = vi / W;
+    const int oh = t2 % H;
+    const int od = t2 / H;
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = s_b[c];
@@ -130,22 +131,39 @@ __global__ void __launch_bounds__(256) wgrad_smallcin_kernel(const TA* __restric
 #pragma unroll
   for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
   if (vslot < slots) {
-    for (long long gv = (long long)blockIdx.x * slots + vslot; gv < NV; gv += (long long)gridDim.x * slots) {
-      const int n = (int)(gv / V);
-      const long long o = gv - (long long)n * V;
-      const int ow = (int)(o % W), oh = (int)((o / W) % H), od = (int)(o / ((long long)W * H));
-      const int id = od + cd, ih = oh + ch_, iw = ow + cw;
-      float xv = 0.f;
-      if (active && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
-        xv = to_f(a[((((long long)n * D + id) * H + ih) * W + iw) * ald + ci]);
+    // each voxel slot walks a contiguous chunk: coordinates advance incrementally (no per-voxel division)
+    const long long nslots = (long long)gridDim.x * slots;
+    const long long chunk = (NV + nslots - 1) / nslots;
+    long long gv = ((long long)blockIdx.x * slots + vslot) * chunk;
+    long long gend = gv + chunk < NV ? gv + chunk : NV;
+    if (gv < gend) {
+      int n = (int)(gv / V);
+      long long o = gv - (long long)n * V;
+      int ow = (int)(o % W), oh = (int)((o / W) % H), od = (int)(o / ((long long)W * H));
       const TB* pb = b + gv * bld;
+      for (; gv < gend; ++gv, pb += bld) {
+        const int id = od + cd, ih = oh + ch_, iw = ow + cw;
+        float xv = 0.f;
+        if (active && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+          xv = to_f(a[((((long long)n * D + id) * H + ih) * W + iw) * ald + ci]);
 #pragma unroll
-      for (int c4 = 0; c4 < COUT / 4; ++c4) {
-        const float4 dv = load4(pb + 4 * c4);
-        acc[4 * c4 + 0] = fmaf(xv, dv.x, acc[4 * c4 + 0]);
-        acc[4 * c4 + 1] = fmaf(xv, dv.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(xv, dv.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(xv, dv.w, acc[4 * c4 + 3]);
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 dv = load4(pb + 4 * c4);
+          acc[4 * c4 + 0] = fmaf(xv, dv.x, acc[4 * c4 + 0]);
+          acc[4 * c4 + 1] = fmaf(xv, dv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(xv, dv.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(xv, dv.w, acc[4 * c4 + 3]);
+        }
+        if (++ow == W) {
+          ow = 0;
+          if (++oh == H) {
+            oh = 0;
+            if (++od == D) {
+              od = 0;
+              ++n;
+            }
+          }
+        }
       }
     }
   }
