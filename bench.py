@@ -390,12 +390,13 @@ def main():
     graphed = None
     if use_graph:
         try:
+            # data parallel: GraphedStep keeps the NCCL collectives outside its two graphs (split mode), so a
+            # rank that has to fall back to eager launches still issues the same collectives in the same order
             graphed = GraphedStep(model, lossfn, x, y, warmup=1)
         except Exception as e:  # pragma: no cover
-            if rank == 0:
-                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches",
-                      file=sys.stderr)
-            use_graph = False
+            print(f"[bench] rank {rank}: CUDA graph capture failed ({type(e).__name__}: {e}); eager launches",
+                  file=sys.stderr)
+            graphed = GraphedStep(model, lossfn, x, y, warmup=1, use_graph=False)
             torch.cuda.synchronize()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -420,7 +421,7 @@ def main():
 
     def resident_step():
         if use_graph:
-            graphed.graph.replay()
+            graphed()                      # replays on the static (HBM-resident) input buffers
         else:
             eager_step(x, y)
 
@@ -432,6 +433,7 @@ def main():
         else:
             loss = eager_step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
         host_loss.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller has the loss value on the host
 
     for _ in range(args.warmup):
         resident_step()
@@ -490,7 +492,8 @@ def main():
                                    + (" + NCCL SUM all-reduce of the flat fp32 gradient bucket" if world > 1 else ""),
                        "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
                        "l2": "256 MiB flush before every timed step; per-step working set > 1 GB >> 126 MB L2",
-                       "cuda_graph": use_graph, "precision_mode": args.precision},
+                       "cuda_graph": bool(use_graph and (graphed.graph is not None or graphed.graph_a is not None)),
+                       "precision_mode": args.precision},
             "e2e": {"value": vox_step / t_e2e, "unit": "voxels/s", "ms_per_step": t_e2e * 1e3,
                     "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,

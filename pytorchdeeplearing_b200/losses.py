@@ -67,6 +67,21 @@ class _FusedLoss(torch.autograd.Function):
         return dz.permute(*inv), None, None, None, None, None
 
 
+def loss_spec(lossfn):
+    """(terms, alpha, gamma, alpha_f) of one of the loss modules below (used by graphed.GraphedStep)."""
+    name = type(lossfn).__name__
+    table = {"BinaryDiceLoss": DICE, "BinaryCrossEntropyLoss": CE, "BinaryFocalLoss": FOCAL,
+             "BinaryCrossEntropyDiceLoss": DICE | CE, "BinaryDiceFocalLoss": DICE | FOCAL,
+             "MutilCrossEntropyLoss": CE, "MutilFocalLoss": FOCAL, "MutilDiceLoss": DICE,
+             "MutilCrossEntropyDiceLoss": DICE | CE}
+    if name not in table:
+        raise TypeError(f"{name} is not a pytorchdeeplearing_b200 loss")
+    alpha = getattr(lossfn, "alpha", None) if name.startswith("Mutil") and (table[name] & DICE) else None
+    gamma = float(getattr(lossfn, "gamma", 2.0))
+    alpha_f = float(getattr(lossfn, "alpha", 0.25)) if name in ("BinaryFocalLoss", "BinaryDiceFocalLoss") else 0.25
+    return table[name], alpha, gamma, alpha_f
+
+
 def _call(logits, labels, terms, alpha=None, gamma=2.0, alpha_f=0.25):
     return _FusedLoss.apply(logits, labels, terms, alpha, gamma, alpha_f)
 

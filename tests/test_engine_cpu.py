@@ -146,3 +146,32 @@ def test_cpu_tensor_without_backend_fails_loudly():
         m(torch.zeros(1, 1, 16, 16))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         b200.BinaryDiceLoss()(torch.zeros(1, 1, 16, 16), torch.zeros(1, 16, 16, dtype=torch.long))
+
+
+def test_graphed_step_split_phases_match_autograd_path():
+    """GraphedStep's split (data-parallel) mode drives the engine directly; it must give the same loss and
+    gradients as the autograd path (world size 1 gloo group so the collectives are identities)."""
+    import torch.distributed as dist
+    from pytorchdeeplearing_b200.graphed import GraphedStep
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29700 + os.getpid() % 200))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        spec, sd, model, ofwd, draw = _build("vnet3d", 1, 2, seed=5)
+        model.eval()
+        x, y = oracle.make_inputs(2, 1, (16, 16, 16), 2, seed=77)
+        lossfn = b200.MutilCrossEntropyDiceLoss(torch.linspace(0.5, 1.5, 2))
+        logits, _ = model(x)
+        loss = lossfn(logits, y)
+        loss.backward()
+        ref = {n: p.grad.clone() for n, p in model.named_parameters()}
+        b200.enable_data_parallel()
+        step = GraphedStep(model, lossfn, x, y, warmup=1, use_graph=False)
+        loss2 = step(x, y)
+        b200.disable_data_parallel()
+        assert abs(loss2.item() - loss.item()) < 1e-6
+        for n, p in model.named_parameters():
+            assert (p.grad - ref[n]).norm() <= 1e-5 * (ref[n].norm() + 1e-12), n
+    finally:
+        b200.disable_data_parallel()
+        dist.destroy_process_group()
