@@ -351,6 +351,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         b200.enable_data_parallel()
     b200.set_precision(args.precision)

@@ -141,29 +141,48 @@ __global__ void __launch_bounds__(256) wgrad_smallcin_kernel(const TA* __restric
       long long o = gv - (long long)n * V;
       int ow = (int)(o % W), oh = (int)((o / W) % H), od = (int)(o / ((long long)W * H));
       const TB* pb = b + gv * bld;
-      for (; gv < gend; ++gv, pb += bld) {
-        const int id = od + cd, ih = oh + ch_, iw = ow + cw;
-        float xv = 0.f;
-        if (active && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
-          xv = to_f(a[((((long long)n * D + id) * H + ih) * W + iw) * ald + ci]);
+      // 4 voxels per trip: their x / dy loads are all issued before the first FMA (latency overlap)
+      while (gv < gend) {
+        float xv[4];
+        float4 dv[4][COUT / 4];
+        int cnt = 0;
 #pragma unroll
-        for (int c4 = 0; c4 < COUT / 4; ++c4) {
-          const float4 dv = load4(pb + 4 * c4);
-          acc[4 * c4 + 0] = fmaf(xv, dv.x, acc[4 * c4 + 0]);
-          acc[4 * c4 + 1] = fmaf(xv, dv.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(xv, dv.z, acc[4 * c4 + 2]);
-          acc[4 * c4 + 3] = fmaf(xv, dv.w, acc[4 * c4 + 3]);
-        }
-        if (++ow == W) {
-          ow = 0;
-          if (++oh == H) {
-            oh = 0;
-            if (++od == D) {
-              od = 0;
-              ++n;
+        for (int u = 0; u < 4; ++u) {
+          xv[u] = 0.f;
+          if (gv + u < gend) {
+            const int id = od + cd, ih = oh + ch_, iw = ow + cw;
+            if (active && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+              xv[u] = to_f(a[((((long long)n * D + id) * H + ih) * W + iw) * ald + ci]);
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 4; ++c4) dv[u][c4] = load4(pb + (long long)u * bld + 4 * c4);
+            ++cnt;
+            if (++ow == W) {
+              ow = 0;
+              if (++oh == H) {
+                oh = 0;
+                if (++od == D) {
+                  od = 0;
+                  ++n;
+                }
+              }
             }
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 4; ++c4) dv[u][c4] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            acc[4 * c4 + 0] = fmaf(xv[u], dv[u][c4].x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(xv[u], dv[u][c4].y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(xv[u], dv[u][c4].z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(xv[u], dv[u][c4].w, acc[4 * c4 + 3]);
+          }
+        }
+        gv += cnt;
+        pb += (long long)cnt * bld;
       }
     }
   }
