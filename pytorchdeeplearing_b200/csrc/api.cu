@@ -36,6 +36,19 @@ int smallcin_conv(int kind, int dims, const b200seg_tensor* x, const void* w, in
 int smallcin_wgrad_supported(int kind, const b200seg_tensor* a, const b200seg_tensor* b);
 int smallcin_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
                    cudaStream_t st);
+int stem_mma_conv_supported(int kind, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                            const b200seg_tensor* addend);
+int stem_mma_conv(int kind, int dims, const b200seg_tensor* x, const void* w, const float* bias,
+                  const b200seg_tensor* y, double* stats, int device, cudaStream_t st);
+int stem_mma_wgrad_supported(int kind, const b200seg_tensor* a, const b200seg_tensor* b);
+int stem_mma_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+                   cudaStream_t st);
+int stem_conv_supported(int kind, const b200seg_tensor* x, const b200seg_tensor* y, const b200seg_tensor* addend);
+int stem_conv(int kind, int dims, const b200seg_tensor* x, const void* w, int w_dtype, const float* bias,
+              const b200seg_tensor* y, double* stats, int device, cudaStream_t st);
+int stem_wgrad_supported(int kind, const b200seg_tensor* a, const b200seg_tensor* b);
+int stem_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+               cudaStream_t st);
 int head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* logits, float* probs, int nc,
              int device, cudaStream_t st);
 int head_bwd_supported(const b200seg_tensor* x, int nc);
@@ -147,8 +160,17 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
   }
   B200_CHECK_ARG(w_dtype != B200SEG_BF16_TC && w_dtype != B200SEG_BF16_HALO,
                  "b200seg_conv: B200SEG_BF16_TC weights need bf16, 16-byte aligned activations of a supported shape");
-  if (smallcin_conv_supported(kind, x, y, addend) &&
-      (w_dtype == B200SEG_F32 ? (x->dtype == B200SEG_F32 && y->dtype == B200SEG_F32) : y->dtype == B200SEG_BF16))
+  static const bool stem_off = [] {
+    const char* e = getenv("B200SEG_DISABLE_STEM");
+    return e && e[0] == '1';
+  }();
+  const bool small_types =
+      w_dtype == B200SEG_F32 ? (x->dtype == B200SEG_F32 && y->dtype == B200SEG_F32) : y->dtype == B200SEG_BF16;
+  if (!stem_off && stem_mma_conv_supported(kind, x, w_dtype, y, addend))
+    return stem_mma_conv(kind, dims, x, wpk, bias, y, stats, device, ST(stream));
+  if (!stem_off && small_types && stem_conv_supported(kind, x, y, addend))
+    return stem_conv(kind, dims, x, wpk, w_dtype, bias, y, stats, device, ST(stream));
+  if (small_types && smallcin_conv_supported(kind, x, y, addend))
     return smallcin_conv(kind, dims, x, wpk, w_dtype, bias, y, stats, device, ST(stream));
   return conv_generic(kind, dims, x, wpk, w_dtype, bias, y, stats, addend, ST(stream));
 }
@@ -173,6 +195,13 @@ int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_ten
     if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
     return wgrad_tc(kind, dims, a, b, dwp, device, ST(stream));
   }
+  static const bool stem_off = [] {
+    const char* e = getenv("B200SEG_DISABLE_STEM");
+    return e && e[0] == '1';
+  }();
+  if (!stem_off && stem_mma_wgrad_supported(kind, a, b))
+    return stem_mma_wgrad(kind, dims, a, b, dwp, device, ST(stream));
+  if (!stem_off && stem_wgrad_supported(kind, a, b)) return stem_wgrad(kind, dims, a, b, dwp, device, ST(stream));
   if (smallcin_wgrad_supported(kind, a, b)) return smallcin_wgrad(kind, dims, a, b, dwp, device, ST(stream));
   return wgrad_generic(kind, dims, a, b, dwp, device, ST(stream));
 }

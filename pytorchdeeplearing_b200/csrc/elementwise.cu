@@ -53,15 +53,47 @@ struct PackDesc {            // mirrors b200seg_pack_desc (include/b200seg.h)
   int block_start, nblocks;
 };
 
+constexpr int kPackCols = 64;        // columns (k, n2, n1) staged per tile in the tap-contiguous paths
+constexpr int kPackMaxT = 27;
+
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  __shared__ float s_tile[kPackMaxT][kPackCols + 1];
   int lo = 0, hi = count - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const PackDesc d = table[lo];
-  const long long total = (long long)d.T * d.K * d.N2 * d.N1;
   const int b = blockIdx.x - d.block_start;
+  if (d.st == 1 && d.T > 1 && d.T <= kPackMaxT) {
+    // torch conv weights keep the taps contiguous ([co][ci][taps]): read whole tap runs (T*4 bytes per column),
+    // transpose through shared memory, write the destination rows [t][cols] with unit stride.
+    const int T = d.T;
+    const long long J = (long long)d.K * d.N2 * d.N1;                 // destination columns
+    for (long long j0 = (long long)b * kPackCols; j0 < J; j0 += (long long)d.nblocks * kPackCols) {
+      const int ncol = (int)(J - j0 < kPackCols ? J - j0 : kPackCols);
+      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
+        const int jl = idx / T, ts = idx - jl * T;
+        const long long j = j0 + jl;
+        const int n1 = (int)(j % d.N1);
+        const long long r = j / d.N1;
+        const int n2 = (int)(r % d.N2);
+        const int k = (int)(r / d.N2);
+        s_tile[d.flip ? T - 1 - ts : ts][jl] = d.src[ts + k * d.sk + n2 * d.sn2 + n1 * d.sn1];
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
+        const int t = idx / ncol, jl = idx - t * ncol;
+        const float v = s_tile[t][jl];
+        const long long o = (long long)t * J + j0 + jl;
+        if (d.out_dtype == B200SEG_BF16) static_cast<bf16*>(d.dst)[o] = __float2bfloat16_rn(v);
+        else static_cast<float*>(d.dst)[o] = v;
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  const long long total = (long long)d.T * d.K * d.N2 * d.N1;
   for (long long i = b * 256LL + threadIdx.x; i < total; i += (long long)d.nblocks * 256) {
     const int n1 = (int)(i % d.N1);
     long long r = i / d.N1;
@@ -78,15 +110,38 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
 
 // unpack: dst[t*st + k*sk + n*sn2] = src[(t*K + k)*N2 + n]   (N1 unused = 1)
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  __shared__ float s_tile[kPackMaxT][kPackCols + 1];
   int lo = 0, hi = count - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const PackDesc d = table[lo];
-  const long long total = (long long)d.T * d.K * d.N2;
   const int b = blockIdx.x - d.block_start;
   float* out = static_cast<float*>(d.dst);
+  if (d.st == 1 && d.T > 1 && d.T <= kPackMaxT) {
+    // source rows [t][cols] are read with unit stride, the torch gradient gets whole tap runs per column
+    const int T = d.T;
+    const long long J = (long long)d.K * d.N2;
+    for (long long j0 = (long long)b * kPackCols; j0 < J; j0 += (long long)d.nblocks * kPackCols) {
+      const int ncol = (int)(J - j0 < kPackCols ? J - j0 : kPackCols);
+      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
+        const int t = idx / ncol, jl = idx - t * ncol;
+        s_tile[t][jl] = d.src[(long long)t * J + j0 + jl];
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
+        const int jl = idx / T, t = idx - jl * T;
+        const long long j = j0 + jl;
+        const int n = (int)(j % d.N2);
+        const int k = (int)(j / d.N2);
+        out[t + k * d.sk + n * d.sn2] = s_tile[t][jl];
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  const long long total = (long long)d.T * d.K * d.N2;
   for (long long i = b * 256LL + threadIdx.x; i < total; i += (long long)d.nblocks * 256) {
     const int n = (int)(i % d.N2);
     const long long r = i / d.N2;
@@ -219,6 +274,94 @@ __device__ __forceinline__ void gn_bwd_coef_from_sums(const GnRef& r, const doub
   }
 }
 
+// Block-cooperative form used by the kernels: the coefficients of ALL C channels of sample n at once.
+// Every global operand (statistics, backward sums, gamma, beta, dropout scale) is fetched in ONE round of
+// independent loads, one thread per channel; the per-group sums then run over shared memory in fixed channel
+// order.  (The per-thread forms above walk the group's channels with dependent global loads -- ~cpg L2
+// latencies per CTA, which is the whole run time of the kernels of the small pyramid levels.)
+//   s_d : double scratch, (BWD ? 4 : 2) * C + 4 * groups;  on return s_d[GRP..] = {mean, rstd, m1, m2} per group
+//   s_f : float scratch, 3 * C  (scale, gamma, beta)
+//   A, B (and P, Q, R when BWD): outputs, C floats each (shared memory)
+__host__ __device__ inline size_t gn_cta_doubles(int C, int groups, bool bwd) { return (size_t)(bwd ? 4 : 2) * C + 4 * groups; }
+
+template <bool BWD>
+__device__ __forceinline__ double* gn_cta_coefs(const GnRef& r, const double* __restrict__ sums, int n, int C,
+                                                double* s_d, float* s_f, float* A, float* B, float* P, float* Q,
+                                                float* R) {
+  const int cpg = C / r.groups;
+  double* d0 = s_d;
+  double* d1 = s_d + C;
+  double* d2 = s_d + 2 * C;           // BWD only
+  double* d3 = s_d + 3 * C;           // BWD only
+  double* grp = s_d + (BWD ? 4 : 2) * C;
+  float* f_sc = s_f;
+  float* f_ga = s_f + C;
+  float* f_be = s_f + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double* p = r.stats + ((long long)n * C + c) * 2;
+    d0[c] = p[0];
+    d1[c] = p[1];
+    f_sc[c] = r.scale ? r.scale[(long long)n * C + c] : 1.f;
+    f_ga[c] = r.gamma[c];
+    f_be[c] = r.beta[c];
+    if (BWD) {
+      const double* q = sums + ((long long)n * C + c) * 3;
+      d2[c] = q[0];
+      d3[c] = q[1];
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < r.groups) {
+    const int g = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      s += d0[g * cpg + k];
+      q += d1[g * cpg + k];
+    }
+    const double mean = s / r.m;
+    double var = q / r.m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    grp[g * 4 + 0] = mean;
+    grp[g * 4 + 1] = rsqrt(var + (double)r.eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = grp[g * 4 + 0], rstd = grp[g * 4 + 1];
+    const double sc = (double)f_sc[c], ga = (double)f_ga[c], be = (double)f_be[c];
+    A[c] = (float)(rstd * ga * sc);
+    B[c] = (float)((be - mean * rstd * ga) * sc);
+    if (BWD) {
+      const double s1 = d2[c] * sc, s2 = d3[c] * sc;
+      d2[c] = ga * s1;
+      d3[c] = ga * rstd * (s2 - mean * s1);
+    }
+  }
+  if (BWD) {
+    __syncthreads();
+    if ((int)threadIdx.x < r.groups) {
+      const int g = threadIdx.x;
+      double sa = 0.0, sax = 0.0;
+      for (int k = 0; k < cpg; ++k) {
+        sa += d2[g * cpg + k];
+        sax += d3[g * cpg + k];
+      }
+      grp[g * 4 + 2] = sa / r.m;
+      grp[g * 4 + 3] = sax / r.m;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double mu = grp[g * 4 + 0], rs = grp[g * 4 + 1], m1 = grp[g * 4 + 2], m2 = grp[g * 4 + 3];
+      P[c] = (float)(rs * (double)f_ga[c] * (double)f_sc[c]);
+      Q[c] = (float)(-rs * rs * m2);
+      R[c] = (float)(-rs * m1 + rs * rs * mu * m2);
+    }
+  }
+  __syncthreads();
+  return grp;
+}
+
 // ---------------------------------------------------------------------------------------------
 // vector helpers: VEC channels of type T <-> float[VEC]
 // ---------------------------------------------------------------------------------------------
@@ -265,20 +408,13 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
   EW_PROLOGUE(C)
   float A1[VEC], B1[VEC], A2[VEC], B2[VEC];
   if (gn1.stats != nullptr) {
-    // coefficients once per CTA (one thread per channel), then broadcast through shared memory
-    extern __shared__ float s_cf[];                       // [4][C]: A1, B1, A2, B2
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float a_, b_;
-      gn_coef_from_stats<1>(gn1, n, C, c, &a_, &b_, nullptr, nullptr);
-      s_cf[c] = a_;
-      s_cf[C + c] = b_;
-      if (y2 != nullptr) {
-        gn_coef_from_stats<1>(gn2, n, C, c, &a_, &b_, nullptr, nullptr);
-        s_cf[2 * C + c] = a_;
-        s_cf[3 * C + c] = b_;
-      }
-    }
-    __syncthreads();
+    // coefficients once per CTA (block-cooperative), then broadcast through shared memory
+    extern __shared__ double s_dyn[];
+    double* s_d = s_dyn;                                                  // scratch doubles
+    float* s_f = reinterpret_cast<float*>(s_d + gn_cta_doubles(C, gn1.groups > gn2.groups ? gn1.groups : gn2.groups, false));
+    float* s_cf = s_f + 3 * C;                                            // [4][C]: A1, B1, A2, B2
+    gn_cta_coefs<false>(gn1, nullptr, n, C, s_d, s_f, s_cf, s_cf + C, nullptr, nullptr, nullptr);
+    if (y2 != nullptr) gn_cta_coefs<false>(gn2, nullptr, n, C, s_d, s_f, s_cf + 2 * C, s_cf + 3 * C, nullptr, nullptr, nullptr);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       A1[j] = s_cf[c0 + j];
@@ -334,25 +470,24 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
                                                             double* __restrict__ sums, int C, long long V,
                                                             const GnRef gn, const int staged) {
   EW_PROLOGUE(C)
-  extern __shared__ double s_redd[];   // [3][C]
+  // dynamic smem: doubles [3][C] accumulators | coefficient scratch | [8][3][C] staging (if staged); then floats
+  extern __shared__ double s_redd[];
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_redd[i] = 0.0;
-  __syncthreads();
+  double* s_cd = s_redd + 3 * C;
+  double* s_part = s_cd + gn_cta_doubles(C, gn.groups, false);
+  float* s_cfl = reinterpret_cast<float*>(s_part + (staged ? 8 * 3 * C : 0));
   float A[VEC], B[VEC];
   float f1[VEC], f2[VEC], f3[VEC];
   if (gn.stats != nullptr) {
-    float* s_ab = reinterpret_cast<float*>(s_redd + 3 * C);      // [2][C] after the fp64 scratch
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float a_, b_;
-      gn_coef_from_stats<1>(gn, n, C, c, &a_, &b_, nullptr, nullptr);
-      s_ab[c] = a_;
-      s_ab[C + c] = b_;
-    }
-    __syncthreads();
+    float* s_ab = s_cfl + 3 * C;                                          // [2][C]
+    gn_cta_coefs<false>(gn, nullptr, n, C, s_cd, s_cfl, s_ab, s_ab + C, nullptr, nullptr, nullptr);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       A[j] = s_ab[c0 + j];
       B[j] = s_ab[C + c0 + j];
     }
+  } else {
+    __syncthreads();
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
@@ -401,7 +536,6 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (staged) {
     // every warp covers all C channels with its first G lanes: private rows, no atomics, fixed summation order
-    double* s_part = s_redd + 3 * C + (C + 1) / 2 * 2;      // [8 warps][3][C], after scratch + coefficient floats
     if (lane < lane_groups) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
@@ -492,19 +626,38 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
   EW_PROLOGUE(C)
   float A[VEC], B[VEC], P[VEC], Q[VEC], R[VEC];
   if (gn.stats != nullptr) {
-    extern __shared__ float s_c5[];                       // [5][C]: A, B, P, Q, R of sample n
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float a_, b_, p_, q_, r_;
-      double mu_, rs_;
-      gn_coef_from_stats<1>(gn, n, C, c, &a_, &b_, &mu_, &rs_);
-      gn_bwd_coef_from_sums<1>(gn, sums, n, C, c, &mu_, &rs_, &p_, &q_, &r_);
-      s_c5[c] = a_;
-      s_c5[C + c] = b_;
-      s_c5[2 * C + c] = p_;
-      s_c5[3 * C + c] = q_;
-      s_c5[4 * C + c] = r_;
+    extern __shared__ double s_dyn[];
+    double* s_d = s_dyn;
+    float* s_f = reinterpret_cast<float*>(s_d + gn_cta_doubles(C, gn.groups, true));
+    float* s_c5 = s_f + 3 * C;                            // [5][C]: A, B, P, Q, R
+    // parameter gradients (d gamma, d beta, d bias): the LAST block of the grid, fixed order over the samples
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) {
+      const int cpg = C / gn.groups;
+      const double vox = gn.m / (double)cpg;
+      double dg[2] = {0.0, 0.0}, db[2] = {0.0, 0.0}, dbi[2] = {0.0, 0.0};      // channels tid, tid + 256
+      for (int nn = 0; nn < N; ++nn) {
+        const double* grp = gn_cta_coefs<true>(gn, sums, nn, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C,
+                                               s_c5 + 4 * C);
+        for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
+          const int g = c / cpg;
+          const double mu = grp[g * 4 + 0], rs = grp[g * 4 + 1], m1 = grp[g * 4 + 2], m2 = grp[g * 4 + 3];
+          const double sc = (double)s_f[c], ga = (double)s_f[C + c];
+          const double* sp = sums + ((long long)nn * C + c) * 3;
+          const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
+          const double qd = -rs * rs * m2, rd = -rs * m1 + rs * rs * mu * m2;
+          db[k] += s1;
+          dg[k] += rs * (s2 - mu * s1);
+          dbi[k] += rs * ga * s1 + qd * s3 + rd * vox;
+        }
+        __syncthreads();
+      }
+      for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
+        dgamma[c] += (float)dg[k];
+        dbeta[c] += (float)db[k];
+        if (dbias != nullptr) dbias[c] = (float)dbi[k];
+      }
     }
-    __syncthreads();
+    gn_cta_coefs<true>(gn, sums, n, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C, s_c5 + 4 * C);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       A[j] = s_c5[c0 + j];
@@ -512,29 +665,6 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
       P[j] = s_c5[2 * C + c0 + j];
       Q[j] = s_c5[3 * C + c0 + j];
       R[j] = s_c5[4 * C + c0 + j];
-    }
-    // parameter gradients (d gamma, d beta, d bias): the LAST block of the grid, fixed order over the samples
-    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) {
-      const int cpg = C / gn.groups;
-      const double vox = gn.m / (double)cpg;
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double dg = 0.0, db = 0.0, dbi = 0.0;
-        for (int nn = 0; nn < N; ++nn) {
-          float a1[1], b1[1], p1[1], q1[1], r1[1];
-          double mu1[1], rs1[1], qd[1], rd[1];
-          gn_coef_from_stats<1>(gn, nn, C, c, a1, b1, mu1, rs1);
-          gn_bwd_coef_from_sums<1>(gn, sums, nn, C, c, mu1, rs1, p1, q1, r1, qd, rd);
-          const double sc = gn.scale ? (double)gn.scale[(long long)nn * C + c] : 1.0;
-          const double* sp = sums + ((long long)nn * C + c) * 3;
-          const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
-          db += s1;
-          dg += rs1[0] * (s2 - mu1[0] * s1);
-          dbi += rs1[0] * (double)gn.gamma[c] * s1 + qd[0] * s3 + rd[0] * vox;
-        }
-        dgamma[c] += (float)dg;
-        dbeta[c] += (float)db;
-        if (dbias != nullptr) dbias[c] = (float)dbi;
-      }
     }
   } else {
 #pragma unroll
@@ -801,7 +931,9 @@ int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, co
   EW_DISPATCH(out, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, out->n, device), out->n);
-    apply_kernel<T, VEC><<<grid, 256, 4 * C * sizeof(float), s>>>(
+    const int mg = (g1 && g2 && g2->groups > g1->groups) ? g2->groups : (g1 ? g1->groups : 1);
+    const size_t smem = gn_cta_doubles(C, mg, false) * sizeof(double) + (size_t)7 * C * sizeof(float);
+    apply_kernel<T, VEC><<<grid, 256, smem, s>>>(
         static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
         res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V,
         make_gnref(g1, C), make_gnref(g2, C));
@@ -820,9 +952,18 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
     const bool pow2g = (G & (G - 1)) == 0;
-    const size_t base = 3 * C * sizeof(double) + (size_t)((C + 1) / 2 * 2) * sizeof(double);
+    const int groups = (gn && gn->stats) ? gn->groups : 1;
+    const size_t base = (3 * C + gn_cta_doubles(C, groups, false)) * sizeof(double) + (size_t)5 * C * sizeof(float);
     const size_t staged_bytes = base + (size_t)8 * 3 * C * sizeof(double);
-    const int staged = (pow2g && G <= 32 && staged_bytes <= 44 * 1024) ? 1 : 0;
+    const int staged = (pow2g && G <= 32 && staged_bytes <= 96 * 1024) ? 1 : 0;
+    if (staged && staged_bytes > 48 * 1024) {
+      static int attr_done[64] = {0};                      // per device, per instantiation
+      if (device >= 0 && device < 64 && !attr_done[device]) {
+        B200_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       96 * 1024));
+        attr_done[device] = 1;
+      }
+    }
     gn_bwd_reduce_kernel<T, VEC><<<grid, 256, staged ? staged_bytes : base, s>>>(
         static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
         make_gnref(gn, C), staged);
@@ -850,10 +991,13 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
   const bool vok = vec_ok(g) && vec_ok(y) && vec_ok(dy);
   const long long V = nvox(y);
   const int C = y->c;
+  B200_CHECK_ARG(!(gn && gn->stats) || C <= 512, "gn_bwd_apply: fused coefficients support C <= 512 (got %d)", C);
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device), y->n);
-    gn_bwd_apply_kernel<T, VEC><<<grid, 256, 5 * C * sizeof(float), s>>>(static_cast<const T*>(g->ptr), g->ld,
+    const int groups = (gn && gn->stats) ? gn->groups : 1;
+    const size_t smem = gn_cta_doubles(C, groups, true) * sizeof(double) + (size_t)8 * C * sizeof(float);
+    gn_bwd_apply_kernel<T, VEC><<<grid, 256, smem, s>>>(static_cast<const T*>(g->ptr), g->ld,
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
                                                      static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
                                                      y->n, dgamma, dbeta, dbias);

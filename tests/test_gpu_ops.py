@@ -33,6 +33,11 @@ def rnd(shape, dtype, g, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(dtype)
 
 
+def stem_mma_shape(dtype, cin, sp):
+    """the bf16 stem kernels convert the fp32 image to bf16: feed them bf16-representable inputs"""
+    return dtype == torch.bfloat16 and cin == 1 and sp[2] % 16 == 0 and sp[1] % 8 == 0
+
+
 def sliced(n, sp, c, dtype, g, pad):
     """activation view with channel pitch > C when pad"""
     if pad:
@@ -46,6 +51,15 @@ CONV_CASES = [
     (K3, 3, 2, (6, 10, 12), 16, 16),
     (K3, 3, 1, (5, 7, 9), 32, 32),
     (K3, 3, 1, (4, 6, 8), 1, 16),
+    (K3, 3, 1, (3, 5, 7), 1, 16),            # odd width: one voxel per thread
+    (K3, 3, 2, (20, 24, 28), 1, 16),         # > one grid stride of voxels: coordinate carries in the stem wgrad
+    (K3, 3, 1, (4, 6, 8), 1, 32),
+    (K3, 3, 2, (6, 16, 32), 1, 16),          # bf16: mma.sync stem (W % 16 == 0, H % 8 == 0)
+    (K3, 3, 1, (3, 8, 96), 1, 32),
+    (K3, 2, 2, (1, 24, 48), 1, 32),
+    (K3, 2, 1, (1, 16, 256), 1, 16),         # two tiles along w
+    (K1, 3, 1, (4, 8, 16), 1, 16),
+    (K3, 2, 3, (1, 40, 56), 1, 32),
     (K3, 3, 1, (4, 6, 8), 3, 16),
     (K3, 3, 1, (4, 4, 8), 64, 48),
     (K3, 2, 2, (1, 12, 20), 16, 32),
@@ -84,6 +98,8 @@ def test_conv_forward(be, dtype, kind, dims, n, sp, cin, cout):
     # network-input style x: fp32 even in bf16 mode when cin is not a channel multiple
     xdt = torch.float32 if cin < 16 else dtype
     x = sliced(n, sp, cin, xdt, g, pad=16 if cin >= 16 else 0)
+    if stem_mma_shape(dtype, cin, sp):
+        x = x.bfloat16().float()
     osp = out_spatial(kind, dims, sp)
     ydt = torch.float32 if cout < 16 else dtype
     for with_stats, with_addend in ((True, False), (False, True)):
@@ -119,6 +135,8 @@ def test_conv_dgrad_and_wgrad(be, dtype, kind, dims, n, sp, cin, cout):
     xdt = torch.float32 if cin < 16 else dtype
     gdt = torch.float32 if cout < 16 else dtype
     x = rnd((n,) + sp + (cin,), xdt, g)
+    if stem_mma_shape(dtype, cin, sp):
+        x = x.bfloat16().float()
     dy = rnd((n,) + osp + (cout,), gdt, g)
     # reference via autograd in fp64 on the (rounded) operands
     import torch.nn.functional as F
@@ -342,3 +360,43 @@ def test_groupnorm_fused_coefficient_forms(be, dtype, n, sp, c, masked):
     assert rel(dy_c, dy_e) < tol(dtype, 0.5)
     assert rel(dg_c, dg_e) < 1e-5 and rel(db_c, db_e) < 1e-5
     assert (dbi_c.cpu() - dbi_e).abs().max() < 1e-4 * (1 + dbi_e.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_multi_tensor_pack_and_unpack(be, dtype):
+    """b200seg_pack_weights_multi / b200seg_unpack_wgrads_multi (tap-contiguous smem-transposed paths and the
+    generic path) against the single-tensor entry points, for every operand layout the engine requests."""
+    g = torch.Generator().manual_seed(11)
+    shapes = [(K3, 3, (32, 16, 3, 3, 3), 128 ** 3), (K3, 3, (16, 16, 3, 3, 3), 128 ** 3), (K3, 3, (64, 64, 3, 3, 3), 24 ** 3),
+              (K3, 3, (16, 1, 3, 3, 3), 96 ** 3), (K3, 2, (32, 32, 3, 3), 512 * 512), (K3, 3, (40, 24, 3, 3, 3), 8 ** 3),
+              (K1, 3, (32, 32, 1, 1, 1), 96 ** 3), (K1, 3, (2, 16, 1, 1, 1), 96 ** 3),
+              (DOWN, 3, (32, 16, 2, 2, 2), 48 ** 3), (DOWN, 2, (64, 32, 2, 2), 64 * 64),
+              (UP, 3, (64, 16, 2, 2, 2), 96 ** 3), (UP, 2, (32, 16, 2, 2), 64 * 64)]
+    reqs, singles = [], []
+    for kind, dims, shp, vox in shapes:
+        w = torch.randn(shp, generator=g).cuda()
+        for which in ("fwd", "dgrad"):
+            reqs.append((w, kind, which, dtype, dims, vox))
+    many = be.pack_many(reqs)
+    torch.cuda.synchronize()
+    for (w, kind, which, dt, dims, vox), pm in zip(reqs, many):
+        ps = be.pack_weight(w, kind, which, dt, dims, allow_tc=True, vox=vox)
+        assert pm.code == ps.code and pm.t.shape == ps.t.shape
+        assert torch.equal(pm.t, ps.t), (kind, which, tuple(w.shape))
+    # unpack: [t][k][n] -> parameter layout (n, k, t...)
+    items, refs = [], []
+    for kind, dims, shp, vox in shapes:
+        a, b = shp[0], shp[1]
+        t = 1
+        for q in shp[2:]:
+            t *= q
+        dwp = torch.randn((t, b, a), generator=g).cuda()
+        grad = torch.zeros(shp, device="cuda")
+        ref = torch.zeros(shp, device="cuda")
+        be.unpack_wgrad(dwp, ref, kind, dims)
+        items.append((dwp, grad))
+        refs.append(ref)
+    be.unpack_many(items)
+    torch.cuda.synchronize()
+    for (dwp, grad), ref in zip(items, refs):
+        assert torch.equal(grad, ref), tuple(grad.shape)
