@@ -478,7 +478,12 @@ def main():
         roof.update({"kernel": desc, "launches_per_step": d["n"], "avg_us": dur * 1e6, "traffic": None,
                      "peaks": peaks["source"],
                      "share_of_step": d["ms"] / max(1e-9, sum(v["ms"] for v in kern.values()))})
-        ranked = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:12]
+        ranked_all = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])
+        ranked = ranked_all[:12]
+        if os.environ.get("B200SEG_BENCH_TABLE"):        # development aid: the full per-op table of the eager pass
+            with open(os.environ["B200SEG_BENCH_TABLE"], "w") as f:
+                for k, v in ranked_all:
+                    f.write(f"{v['ms'] * 1e3:9.1f} us  x{v['n']:3d}  {k}\n")
         step_roof = {"hbm_GBps": STEP_MB / 1e3 / t_step, "tflops": STEP_GFLOP / 1e3 / t_step,
                      "frac_hbm": STEP_MB / 1e3 / t_step / peaks["hbm_gbs"],
                      "frac_tensor": STEP_GFLOP / 1e3 / t_step / peaks["bf16_tflops"],

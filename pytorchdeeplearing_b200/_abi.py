@@ -252,7 +252,7 @@ class CudaBackend:
             shape, code, args = self._pack_plan(w, kind, which, dtype, dims, True, vox)
             out = torch.empty(shape, dtype=dtype, device=w.device)
             T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
-            nb = max(1, min(64, (out.numel() + 1023) // 1024))
+            nb = max(1, min(256, (out.numel() + 4095) // 4096))
             descs.append(PackDesc(w.data_ptr(), out.data_ptr(), s_t, s_k, s_n2, s_n1,
                                   F32 if dtype == torch.float32 else BF16, T, K, N2, N1, flip, blocks, nb))
             blocks += nb
@@ -272,7 +272,7 @@ class CudaBackend:
         descs, blocks = [], 0
         for dwp, grad in items:
             t, k, n = dwp.shape
-            nb = max(1, min(64, (dwp.numel() + 1023) // 1024))
+            nb = max(1, min(256, (dwp.numel() + 4095) // 4096))
             descs.append(PackDesc(dwp.data_ptr(), grad.data_ptr(), 1, t, k * t, 0, F32, t, k, n, 1, 0, blocks, nb))
             blocks += nb
         table = self._table_to_device(descs, items[0][0].device)

@@ -15,6 +15,8 @@
 // epilogue (tcgen05.ld -> +bias -> GroupNorm sum/sumsq partials -> +addend -> bf16 NDHWC stores).
 // Two accumulator stages in TMEM overlap the epilogue of tile i with the main loop of tile i+1;
 // CTAs are persistent over contiguous tile ranges (grid = min(tiles, #SM)).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace b200seg {
@@ -57,14 +59,46 @@ struct TcArgs {
   int tw, th, td;         // tiles per dim
   int ntiles;             // N * td * th * tw
   int nstages;
-  int tmem_cols;          // power of two >= 2*Ntile (>= 32)
+  int nacc;               // accumulator stages in TMEM (2 or 4)
+  int tmem_cols;          // power of two >= nacc*Ntile (>= 32)
 };
 
 constexpr int kMaxStages = 8;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 4;          // warps per epilogue group (one per TMEM lane quarter)
+constexpr int kEpiGroups = 2;         // group e drains accumulator stage e: two tiles are in the epilogue at a time
+constexpr int kTcThreads = 64 + 32 * kEpiWarps * kEpiGroups;
+constexpr int kMaxAcc = 4;            // TMEM accumulator stages (the MMA issuer runs this many tiles ahead of the epilogue)
 
-template <int BKC>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// butterfly transpose-reduce of 16 per-lane column values (and their squares) over the 32 lanes of a warp:
+// afterwards every EVEN lane L holds in s[0] / q[0] the warp totals of column stat_col(L)
+__device__ __forceinline__ void stat_butterfly(float* s, float* qq, int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float keep_s = up ? s[j + half] : s[j];
+      const float send_s = up ? s[j] : s[j + half];
+      const float keep_q = up ? qq[j + half] : qq[j];
+      const float send_q = up ? qq[j] : qq[j + half];
+      s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+      qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+    }
+  }
+  s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+  qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+}
+// column owned by an even lane after stat_butterfly: bit k of the index is bit (4-k) of the lane for k = 0..3
+__device__ __forceinline__ int stat_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// NCH > 0 (Cout == 16 * NCH <= 32): the layers with few MACs per output element (1x1x1, 2x2x2 stride 2 and its
+// transpose at 16/32 channels) are bound by the epilogue, so their GroupNorm statistics are accumulated per
+// thread in registers across all of the CTA's tiles and folded over the warp once per sample, and the bias lives
+// in registers.  NCH == 0: generic Cout, per-chunk butterfly.
+template <int BKC, int NCH>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
   constexpr uint32_t SWZ = BKC * 2;                 // bytes per smem row = swizzle span
   constexpr uint32_t A_BYTES = 128u * SWZ;
@@ -77,9 +111,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + kMaxStages;
   uint64_t* tfull = empty + kMaxStages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);     // [4 epilogue warps][2][Cout]
+  uint64_t* tempty = tfull + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);     // [2 groups][4 epilogue warps][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,7 +132,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kMaxAcc; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], kEpiWarps);
     }
@@ -109,7 +143,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * kEpiGroups * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,8 +183,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     uint32_t it = 0;
     int local = 0;
     for (int item = tile_begin; item < tile_end; ++item, ++local) {
-      const uint32_t as = local & 1;
-      const uint32_t aph = (local >> 1) & 1u;
+      const uint32_t as = (uint32_t)local % (uint32_t)p.nacc;
+      const uint32_t aph = ((uint32_t)local / (uint32_t)p.nacc) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * (uint32_t)p.Ntile;
@@ -175,32 +209,59 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   } else {
-    // ===================================================== epilogue warps (2..5)
+    // ===================================================== epilogue warps (2..9), two groups of four
+    const int eg = (warp - 2) >> 2;               // group = accumulator stage it drains
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                // row of the M tile = voxel of the box
     const int rw = row % p.bw;
     const int rh = (row / p.bw) % p.bh;
     const int rd = row / (p.bw * p.bh);
-    const int etid = threadIdx.x - 64;            // 0..127
-    int local = 0;
+    const int etid = (threadIdx.x - 64) & 127;    // 0..127 inside the group
+    float* s_stat_g = s_stat + eg * 8 * p.Cout;   // [4 warps][2][Cout] of this group
     int cur_n = -1;
+    constexpr int NR = NCH > 0 ? NCH : 1;
+    float rs[NR][16], rq[NR][16], rb[NR][16];
+#pragma unroll
+    for (int ci = 0; ci < NR; ++ci)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        rs[ci][j] = 0.f;
+        rq[ci][j] = 0.f;
+        rb[ci][j] = (NCH > 0 && p.bias != nullptr) ? __ldg(p.bias + ci * 16 + j) : 0.f;
+      }
     auto flush_stats = [&](int n) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (NCH > 0 && p.stats != nullptr) {
+#pragma unroll
+        for (int ci = 0; ci < NR; ++ci) {
+          stat_butterfly(rs[ci], rq[ci], lane);
+          if ((lane & 1) == 0) {
+            float* sw_ = s_stat_g + q * 2 * p.Cout;
+            sw_[ci * 16 + stat_col(lane)] += rs[ci][0];
+            sw_[p.Cout + ci * 16 + stat_col(lane)] += rq[ci][0];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            rs[ci][j] = 0.f;
+            rq[ci][j] = 0.f;
+          }
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
       if (p.stats != nullptr && n >= 0) {
         for (int i = etid; i < 2 * p.Cout; i += 128) {
           const int which = i / p.Cout, c = i - which * p.Cout;
           double t = 0.0;
 #pragma unroll
           for (int wq = 0; wq < 4; ++wq) {
-            t += (double)s_stat[wq * 2 * p.Cout + i];
-            s_stat[wq * 2 * p.Cout + i] = 0.f;
+            t += (double)s_stat_g[wq * 2 * p.Cout + i];
+            s_stat_g[wq * 2 * p.Cout + i] = 0.f;
           }
           atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
     };
-    for (int item = tile_begin; item < tile_end; ++item, ++local) {
+    for (int item = tile_begin + eg, local = eg; item < tile_end; item += kEpiGroups, local += kEpiGroups) {
       int t = item / p.ngroups;
       const int ng = item - t * p.ngroups;
       const int iw = t % p.tw; t /= p.tw;
@@ -214,8 +275,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       const int ow = iw * p.bw + rw, oh = ih * p.bh + rh, od = id * p.bd + rd;
       const bool valid = ow < p.W && oh < p.H && od < p.D;
       const long long vox = (((long long)n * p.D + od) * p.H + oh) * p.W + ow;
-      const uint32_t as = local & 1;
-      const uint32_t aph = (local >> 1) & 1u;
+      const uint32_t as = (uint32_t)local % (uint32_t)p.nacc;
+      const uint32_t aph = ((uint32_t)local / (uint32_t)p.nacc) & 1u;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * (uint32_t)p.Ntile + ((uint32_t)(q * 32) << 16);
@@ -233,40 +294,39 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           ovox = (((long long)n * (p.D * p.ud) + (od * p.ud + fa)) * (p.H * p.uh) + (oh * p.uh + fb)) * (p.W * p.uw) +
                  (ow * p.uw + fc);
         }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
-        }
-        if (p.stats != nullptr) {
-          // butterfly transpose-reduce: after 5 steps lane L holds the warp total of column (L>>1)
-          float s[16], qq[16];
+        if (NCH > 0) {
+          const int ci = c0 >> 4;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            s[j] = valid ? v[j] : 0.f;
-            qq[j] = s[j] * s[j];
-          }
-#pragma unroll
-          for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-              const float keep_s = up ? s[j + half] : s[j];
-              const float send_s = up ? s[j] : s[j + half];
-              const float keep_q = up ? qq[j + half] : qq[j];
-              const float send_q = up ? qq[j] : qq[j + half];
-              s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-              qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            v[j] += (NCH == 1 || ci == 0) ? rb[0][j] : rb[NR - 1][j];
+            const float sv = valid ? v[j] : 0.f;
+            if (NCH == 1 || ci == 0) {
+              rs[0][j] += sv;
+              rq[0][j] = fmaf(sv, sv, rq[0][j]);
+            } else {
+              rs[NR - 1][j] += sv;
+              rq[NR - 1][j] = fmaf(sv, sv, rq[NR - 1][j]);
             }
           }
-          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
-          qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
-          if ((lane & 1) == 0) {
-            // column owned by this lane: bit k of the index is bit (4-k) of the lane for k = 0..3
-            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            // this lane is the only writer of its column in this warp's private row: no atomics, fixed order
-            float* sw_ = s_stat + q * 2 * p.Cout;
-            sw_[c0 + col] += s[0];
-            sw_[p.Cout + c0 + col] += qq[0];
+        } else {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+          }
+          if (p.stats != nullptr) {
+            float s[16], qq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              s[j] = valid ? v[j] : 0.f;
+              qq[j] = s[j] * s[j];
+            }
+            stat_butterfly(s, qq, lane);
+            if ((lane & 1) == 0) {
+              // this lane is the only writer of its column in this warp's private row: no atomics, fixed order
+              float* sw_ = s_stat_g + q * 2 * p.Cout;
+              sw_[c0 + stat_col(lane)] += s[0];
+              sw_[p.Cout + c0 + stat_col(lane)] += qq[0];
+            }
           }
         }
         if (valid) {
@@ -363,9 +423,12 @@ int conv_tc_init(int device) {
   if (g_smem_optin[device]) return B200SEG_OK;
   int maxsm = 0;
   B200_CUDA(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+#define TC_ATTR(B, C) \
+  B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm))
+  TC_ATTR(16, 0); TC_ATTR(16, 1); TC_ATTR(16, 2);
+  TC_ATTR(32, 0); TC_ATTR(32, 1); TC_ATTR(32, 2);
+  TC_ATTR(64, 0); TC_ATTR(64, 1); TC_ATTR(64, 2);
+#undef TC_ATTR
   if (wgrad_tc_init(device, maxsm) != B200SEG_OK) return B200SEG_ECUDA;
   g_smem_optin[device] = maxsm;
   return B200SEG_OK;
@@ -415,14 +478,15 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const uint32_t a_bytes = 128u * swz;
   const uint32_t b_bytes = (((uint32_t)p.Ntile * swz) + 1023u) & ~1023u;
   const uint32_t stage = a_bytes + b_bytes;
-  const uint32_t tail = (2 * kMaxStages + 4) * 8 + 16 + 8 * p.Cout * 4;
+  const uint32_t tail = (2 * kMaxStages + 2 * kMaxAcc) * 8 + 16 + 8 * kEpiGroups * p.Cout * 4;
   const int maxsm = g_smem_optin[device] > 0 ? g_smem_optin[device] : 227 * 1024;
   int nst = (int)((maxsm - 1024 - (int)tail - 256) / (int)stage);
   if (nst > kMaxStages) nst = kMaxStages;
   B200_CHECK_ARG(nst >= 2, "conv_tc: tile does not fit in shared memory (Cin=%d Cout=%d)", p.Cin, p.Cout);
   p.nstages = nst;
+  p.nacc = p.Ntile * kMaxAcc <= 512 ? kMaxAcc : 2;
   int cols = 32;
-  while (cols < 2 * p.Ntile) cols *= 2;
+  while (cols < p.nacc * p.Ntile) cols *= 2;
   p.tmem_cols = cols;
   const size_t smem_bytes = 1024 + (size_t)nst * stage + tail + 128;
 
@@ -456,9 +520,21 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   }
   int grid = num_sms(device);
   if (grid > p.ntiles * p.ngroups) grid = p.ntiles * p.ngroups;
-  if (bkc == 64) conv_tc_kernel<64><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
-  else if (bkc == 32) conv_tc_kernel<32><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
-  else conv_tc_kernel<16><<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
+  static const bool regstats_off = [] {
+    const char* e = getenv("B200SEG_TC_REGSTATS");
+    return e && e[0] == '0';
+  }();
+  const int nch = regstats_off ? 0 : (p.Cout == 16 ? 1 : (p.Cout == 32 ? 2 : 0));
+#define TC_LAUNCH(B)                                                                         \
+  do {                                                                                       \
+    if (nch == 1) conv_tc_kernel<B, 1><<<grid, kTcThreads, smem_bytes, st>>>(tmA, tmB, p);          \
+    else if (nch == 2) conv_tc_kernel<B, 2><<<grid, kTcThreads, smem_bytes, st>>>(tmA, tmB, p);     \
+    else conv_tc_kernel<B, 0><<<grid, kTcThreads, smem_bytes, st>>>(tmA, tmB, p);                   \
+  } while (0)
+  if (bkc == 64) TC_LAUNCH(64);
+  else if (bkc == 32) TC_LAUNCH(32);
+  else TC_LAUNCH(16);
+#undef TC_LAUNCH
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

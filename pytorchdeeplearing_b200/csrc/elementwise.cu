@@ -55,39 +55,80 @@ struct PackDesc {            // mirrors b200seg_pack_desc (include/b200seg.h)
 
 constexpr int kPackCols = 64;        // columns (k, n2, n1) staged per tile in the tap-contiguous paths
 constexpr int kPackMaxT = 27;
+constexpr int kPackIters = 8;        // column trips per warp and tile (8 warps, >= 1 column per trip)
 
-__global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int count) {
-  __shared__ float s_tile[kPackMaxT][kPackCols + 1];
+// descriptor owning this block: the block_start column is staged in shared memory with one round of loads
+__device__ __forceinline__ int pack_find_desc(const PackDesc* __restrict__ table, int count, int* s_start) {
   int lo = 0, hi = count - 1;
+  if (count <= 1024) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s_start[i] = table[i].block_start;
+    __syncthreads();
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  }
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
-  const PackDesc d = table[lo];
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  __shared__ float s_tile[kPackMaxT][kPackCols + 1];
+  __shared__ int s_start[1024];
+  const PackDesc d = table[pack_find_desc(table, count, s_start)];
   const int b = blockIdx.x - d.block_start;
   if (d.st == 1 && d.T > 1 && d.T <= kPackMaxT) {
-    // torch conv weights keep the taps contiguous ([co][ci][taps]): read whole tap runs (T*4 bytes per column),
-    // transpose through shared memory, write the destination rows [t][cols] with unit stride.
+    // torch conv weights keep the taps contiguous ([co][ci][taps]): a warp reads whole tap runs (32/T columns per
+    // trip, lane = (column, tap)), the tile is transposed through shared memory and the destination rows
+    // [t][cols] are written with unit stride.  All index arithmetic is 32-bit and per column, not per element.
     const int T = d.T;
-    const long long J = (long long)d.K * d.N2 * d.N1;                 // destination columns
-    for (long long j0 = (long long)b * kPackCols; j0 < J; j0 += (long long)d.nblocks * kPackCols) {
-      const int ncol = (int)(J - j0 < kPackCols ? J - j0 : kPackCols);
-      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
-        const int jl = idx / T, ts = idx - jl * T;
-        const long long j = j0 + jl;
-        const int n1 = (int)(j % d.N1);
-        const long long r = j / d.N1;
-        const int n2 = (int)(r % d.N2);
-        const int k = (int)(r / d.N2);
-        s_tile[d.flip ? T - 1 - ts : ts][jl] = d.src[ts + k * d.sk + n2 * d.sn2 + n1 * d.sn1];
+    const int J = d.K * d.N2 * d.N1;                                  // destination columns
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpw = 32 / T;                                            // columns per warp trip
+    const int sc = lane / T, ts = lane - sc * T;
+    for (int j0 = b * kPackCols; j0 < J; j0 += d.nblocks * kPackCols) {
+      const int ncol = J - j0 < kPackCols ? J - j0 : kPackCols;
+      // all of a warp's column trips are loaded before the first shared-memory store (one latency, not eight)
+      float v[kPackIters];
+#pragma unroll
+      for (int i = 0; i < kPackIters; ++i) {
+        const int jl = warp * cpw + sc + i * 8 * cpw;
+        v[i] = 0.f;
+        if (sc < cpw && jl < ncol) {
+          const int j = j0 + jl;
+          const int n1 = j % d.N1;
+          const int r = j / d.N1;
+          const int n2 = r % d.N2;
+          const int k = r / d.N2;
+          v[i] = d.src[ts + k * d.sk + n2 * d.sn2 + n1 * d.sn1];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kPackIters; ++i) {
+        const int jl = warp * cpw + sc + i * 8 * cpw;
+        if (sc < cpw && jl < ncol) s_tile[d.flip ? T - 1 - ts : ts][jl] = v[i];
       }
       __syncthreads();
-      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
-        const int t = idx / ncol, jl = idx - t * ncol;
-        const float v = s_tile[t][jl];
-        const long long o = (long long)t * J + j0 + jl;
-        if (d.out_dtype == B200SEG_BF16) static_cast<bf16*>(d.dst)[o] = __float2bfloat16_rn(v);
-        else static_cast<float*>(d.dst)[o] = v;
+      if (ncol == kPackCols) {
+        for (int idx = threadIdx.x; idx < kPackCols * T; idx += blockDim.x) {
+          const int t = idx / kPackCols, jl = idx % kPackCols;
+          const float v = s_tile[t][jl];
+          const long long o = (long long)t * J + j0 + jl;
+          if (d.out_dtype == B200SEG_BF16) static_cast<bf16*>(d.dst)[o] = __float2bfloat16_rn(v);
+          else static_cast<float*>(d.dst)[o] = v;
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
+          const int t = idx / ncol, jl = idx - t * ncol;
+          const float v = s_tile[t][jl];
+          const long long o = (long long)t * J + j0 + jl;
+          if (d.out_dtype == B200SEG_BF16) static_cast<bf16*>(d.dst)[o] = __float2bfloat16_rn(v);
+          else static_cast<float*>(d.dst)[o] = v;
+        }
       }
       __syncthreads();
     }
@@ -111,31 +152,46 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
 // unpack: dst[t*st + k*sk + n*sn2] = src[(t*K + k)*N2 + n]   (N1 unused = 1)
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __restrict__ table, int count) {
   __shared__ float s_tile[kPackMaxT][kPackCols + 1];
-  int lo = 0, hi = count - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const PackDesc d = table[lo];
+  __shared__ int s_start[1024];
+  const PackDesc d = table[pack_find_desc(table, count, s_start)];
   const int b = blockIdx.x - d.block_start;
   float* out = static_cast<float*>(d.dst);
   if (d.st == 1 && d.T > 1 && d.T <= kPackMaxT) {
-    // source rows [t][cols] are read with unit stride, the torch gradient gets whole tap runs per column
+    // source rows [t][cols] are read with unit stride; a warp then writes whole tap runs of the torch gradient
     const int T = d.T;
-    const long long J = (long long)d.K * d.N2;
-    for (long long j0 = (long long)b * kPackCols; j0 < J; j0 += (long long)d.nblocks * kPackCols) {
-      const int ncol = (int)(J - j0 < kPackCols ? J - j0 : kPackCols);
-      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
-        const int t = idx / ncol, jl = idx - t * ncol;
-        s_tile[t][jl] = d.src[(long long)t * J + j0 + jl];
+    const int J = d.K * d.N2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpw = 32 / T;
+    const int sc = lane / T, ts = lane - sc * T;
+    for (int j0 = b * kPackCols; j0 < J; j0 += d.nblocks * kPackCols) {
+      const int ncol = J - j0 < kPackCols ? J - j0 : kPackCols;
+      if (ncol == kPackCols) {
+        constexpr int NR = (kPackCols * kPackMaxT + 255) / 256;      // 7 row trips, all loads first
+        float v[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const int idx = threadIdx.x + i * 256;
+          v[i] = idx < kPackCols * T ? d.src[(long long)(idx / kPackCols) * J + j0 + (idx % kPackCols)] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const int idx = threadIdx.x + i * 256;
+          if (idx < kPackCols * T) s_tile[idx / kPackCols][idx % kPackCols] = v[i];
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
+          const int t = idx / ncol, jl = idx - t * ncol;
+          s_tile[t][jl] = d.src[(long long)t * J + j0 + jl];
+        }
       }
       __syncthreads();
-      for (int idx = threadIdx.x; idx < ncol * T; idx += blockDim.x) {
-        const int jl = idx / T, t = idx - jl * T;
-        const long long j = j0 + jl;
-        const int n = (int)(j % d.N2);
-        const int k = (int)(j / d.N2);
-        out[t + k * d.sk + n * d.sn2] = s_tile[t][jl];
+      for (int jl = warp * cpw + sc; jl < ncol; jl += 8 * cpw) {
+        if (sc < cpw) {
+          const int j = j0 + jl;
+          const int n = j % d.N2;
+          const int k = j / d.N2;
+          out[ts + k * d.sk + n * d.sn2] = s_tile[ts][jl];
+        }
       }
       __syncthreads();
     }
@@ -399,7 +455,7 @@ template <typename T> struct Vec<T, 1> {
   (void)total;
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, long long ld1,
+__global__ void __launch_bounds__(256, 3) apply_kernel(const T* __restrict__ y1, long long ld1,
                                                     const float* __restrict__ coef1, const T* __restrict__ y2,
                                                     long long ld2, const float* __restrict__ coef2,
                                                     const T* __restrict__ res, long long ldr, T* __restrict__ out,
@@ -438,8 +494,41 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
       }
     }
   }
-  for (; vi < V; vi += vstep) {
-    const long long vox = (long long)n * V + vi;
+  // two trips of loads in flight per thread (the grid is sized to the resident CTAs, see ew_apply)
+  const long long nb = (long long)n * V;
+  for (; vi + vstep < V; vi += 2 * vstep) {
+    const long long v0 = nb + vi, v1 = v0 + vstep;
+    float a0[VEC], a1[VEC], o0[VEC], o1[VEC];
+    Vec<T, VEC>::load(y1 + v0 * ld1 + c0, a0);
+    Vec<T, VEC>::load(y1 + v1 * ld1 + c0, a1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      o0[j] = fmaxf(fmaf(a0[j], A1[j], B1[j]), 0.f);
+      o1[j] = fmaxf(fmaf(a1[j], A1[j], B1[j]), 0.f);
+    }
+    if (y2 != nullptr) {
+      Vec<T, VEC>::load(y2 + v0 * ld2 + c0, a0);
+      Vec<T, VEC>::load(y2 + v1 * ld2 + c0, a1);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        o0[j] += fmaxf(fmaf(a0[j], A2[j], B2[j]), 0.f);
+        o1[j] += fmaxf(fmaf(a1[j], A2[j], B2[j]), 0.f);
+      }
+    }
+    if (res != nullptr) {
+      Vec<T, VEC>::load(res + v0 * ldr + c0, a0);
+      Vec<T, VEC>::load(res + v1 * ldr + c0, a1);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        o0[j] += a0[j];
+        o1[j] += a1[j];
+      }
+    }
+    Vec<T, VEC>::store(out + v0 * ldo + c0, o0);
+    Vec<T, VEC>::store(out + v1 * ldo + c0, o1);
+  }
+  if (vi < V) {
+    const long long vox = nb + vi;
     float a[VEC], o[VEC];
     Vec<T, VEC>::load(y1 + vox * ld1 + c0, a);
 #pragma unroll
@@ -459,27 +548,29 @@ __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ y1, lo
 }
 
 // sums[n][c] += { sum g*m, sum g*m*y, sum y }, m = [y*A + B > 0]
-// The projection coefficients of the GroupNorm backward are means of these sums and their error is
-// amplified coherently over every voxel by the weight-gradient reduction, so the accumulation runs in
-// fp64 from the first add: fp64 per-thread partials -> shuffle across the lanes that share a channel
-// group -> low-contention fp64 shared atomics -> one fp64 global atomic per (channel, sum) per CTA.
+// The projection coefficients of the GroupNorm backward are means of these sums.  A thread's own partial (a few
+// dozen voxels) and the fold over the lanes of a warp that share its channel group run in fp32; everything after
+// that -- across the 8 warps, across CTAs -- is accumulated in fp64 in a fixed order (one private shared-memory
+// row per warp, then ONE fp64 global atomic per (channel, sum) per CTA).  The grid is sized to the resident CTAs
+// (3 per SM) and the voxel loop keeps two trips of loads in flight: the kernel is a pure HBM stream.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict__ g, long long ldg,
-                                                            const T* __restrict__ y, long long ldy,
-                                                            const float* __restrict__ coef,
-                                                            double* __restrict__ sums, int C, long long V,
-                                                            const GnRef gn, const int staged) {
+__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const T* __restrict__ g, long long ldg,
+                                                               const T* __restrict__ y, long long ldy,
+                                                               const float* __restrict__ coef,
+                                                               double* __restrict__ sums, int C, long long V,
+                                                               const GnRef gn, const int staged) {
   EW_PROLOGUE(C)
-  // dynamic smem: doubles [3][C] accumulators | coefficient scratch | [8][3][C] staging (if staged); then floats
+  // dynamic smem: doubles [3][C] accumulators (unstaged path) | coefficient scratch; then floats: scratch [3][C],
+  // A/B [2][C], staging [8 warps][3][C] (if staged)
   extern __shared__ double s_redd[];
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_redd[i] = 0.0;
   double* s_cd = s_redd + 3 * C;
-  double* s_part = s_cd + gn_cta_doubles(C, gn.groups, false);
-  float* s_cfl = reinterpret_cast<float*>(s_part + (staged ? 8 * 3 * C : 0));
+  float* s_cfl = reinterpret_cast<float*>(s_cd + gn_cta_doubles(C, gn.groups, false));
+  float* s_ab = s_cfl + 3 * C;                                            // [2][C]
+  float* s_part = s_ab + 2 * C;                                           // [8][3][C]
   float A[VEC], B[VEC];
   float f1[VEC], f2[VEC], f3[VEC];
   if (gn.stats != nullptr) {
-    float* s_ab = s_cfl + 3 * C;                                          // [2][C]
     gn_cta_coefs<false>(gn, nullptr, n, C, s_cd, s_cfl, s_ab, s_ab + C, nullptr, nullptr, nullptr);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -498,13 +589,27 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
     }
     f1[j] = f2[j] = f3[j] = 0.f;
   }
-  // a thread sees only ~10 voxel groups (grid sized to the chip): its partial sums stay in fp32, everything
-  // after that (cross-lane, cross-warp, cross-CTA) is accumulated in fp64
-  for (; vi < V; vi += vstep) {
-    const long long vox = (long long)n * V + vi;
+  const T* yb = y + (long long)n * V * ldy + c0;
+  const T* gb = g + (long long)n * V * ldg + c0;
+  for (; vi + vstep < V; vi += 2 * vstep) {
+    float y0[VEC], g0[VEC], y1[VEC], g1[VEC];
+    Vec<T, VEC>::load(yb + vi * ldy, y0);
+    Vec<T, VEC>::load(gb + vi * ldg, g0);
+    Vec<T, VEC>::load(yb + (vi + vstep) * ldy, y1);
+    Vec<T, VEC>::load(gb + (vi + vstep) * ldg, g1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float d0 = fmaf(y0[j], A[j], B[j]) > 0.f ? g0[j] : 0.f;
+      const float d1 = fmaf(y1[j], A[j], B[j]) > 0.f ? g1[j] : 0.f;
+      f1[j] += d0 + d1;
+      f2[j] = fmaf(d0, y0[j], fmaf(d1, y1[j], f2[j]));
+      f3[j] += y0[j] + y1[j];
+    }
+  }
+  if (vi < V) {
     float yv[VEC], gv[VEC];
-    Vec<T, VEC>::load(y + vox * ldy + c0, yv);
-    Vec<T, VEC>::load(g + vox * ldg + c0, gv);
+    Vec<T, VEC>::load(yb + vi * ldy, yv);
+    Vec<T, VEC>::load(gb + vi * ldg, gv);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] : 0.f;
@@ -513,53 +618,45 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
       f3[j] += yv[j];
     }
   }
-  double s1[VEC], s2[VEC], s3[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    s1[j] = (double)f1[j];
-    s2[j] = (double)f2[j];
-    s3[j] = (double)f3[j];
-  }
   // lanes l and l ^ off share the channel group when off is a multiple of G (G a power of two <= 16)
   const bool pow2 = (G & (G - 1)) == 0;
   const int lane_groups = (pow2 && G < 32) ? G : 32;
-  if (lane_groups < 32) {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      for (int off = 16; off >= lane_groups; off >>= 1) {
-        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-        s3[j] += __shfl_xor_sync(0xffffffffu, s3[j], off);
-      }
-    }
-  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (staged) {
+    if (lane_groups < 32) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        for (int off = 16; off >= lane_groups; off >>= 1) {
+          f1[j] += __shfl_xor_sync(0xffffffffu, f1[j], off);
+          f2[j] += __shfl_xor_sync(0xffffffffu, f2[j], off);
+          f3[j] += __shfl_xor_sync(0xffffffffu, f3[j], off);
+        }
+      }
+    }
     // every warp covers all C channels with its first G lanes: private rows, no atomics, fixed summation order
     if (lane < lane_groups) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        s_part[(wid * 3 + 0) * C + c0 + j] = s1[j];
-        s_part[(wid * 3 + 1) * C + c0 + j] = s2[j];
-        s_part[(wid * 3 + 2) * C + c0 + j] = s3[j];
+        s_part[(wid * 3 + 0) * C + c0 + j] = f1[j];
+        s_part[(wid * 3 + 1) * C + c0 + j] = f2[j];
+        s_part[(wid * 3 + 2) * C + c0 + j] = f3[j];
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
       const int k = i / C, c = i - k * C;
       double t = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[(w * 3 + k) * C + c];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)s_part[(w * 3 + k) * C + c];
       atomicAdd(sums + ((long long)n * C + c) * 3 + k, t);
     }
     return;
   }
-  if (lane < lane_groups) {
+  // general channel counts: fp64 shared-memory atomics
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      atomicAdd(&s_redd[0 * C + c0 + j], s1[j]);
-      atomicAdd(&s_redd[1 * C + c0 + j], s2[j]);
-      atomicAdd(&s_redd[2 * C + c0 + j], s3[j]);
-    }
+  for (int j = 0; j < VEC; ++j) {
+    atomicAdd(&s_redd[0 * C + c0 + j], (double)f1[j]);
+    atomicAdd(&s_redd[1 * C + c0 + j], (double)f2[j]);
+    atomicAdd(&s_redd[2 * C + c0 + j], (double)f3[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
@@ -615,7 +712,7 @@ __global__ void gn_bwd_finalize_kernel(const double* __restrict__ sums, const fl
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__ g, long long ldg,
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const T* __restrict__ g, long long ldg,
                                                            const T* __restrict__ y, long long ldy,
                                                            const float* __restrict__ coef,
                                                            const float* __restrict__ coef3, T* __restrict__ dy,
@@ -678,8 +775,26 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
       R[j] = q[2];
     }
   }
-  for (; vi < V; vi += vstep) {
-    const long long vox = (long long)n * V + vi;
+  const long long nb = (long long)n * V;
+  for (; vi + vstep < V; vi += 2 * vstep) {
+    const long long v0 = nb + vi, v1 = v0 + vstep;
+    float y0[VEC], g0[VEC], y1[VEC], g1[VEC];
+    Vec<T, VEC>::load(y + v0 * ldy + c0, y0);
+    Vec<T, VEC>::load(g + v0 * ldg + c0, g0);
+    Vec<T, VEC>::load(y + v1 * ldy + c0, y1);
+    Vec<T, VEC>::load(g + v1 * ldg + c0, g1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float d0 = fmaf(y0[j], A[j], B[j]) > 0.f ? g0[j] * P[j] : 0.f;
+      const float d1 = fmaf(y1[j], A[j], B[j]) > 0.f ? g1[j] * P[j] : 0.f;
+      g0[j] = d0 + fmaf(y0[j], Q[j], R[j]);
+      g1[j] = d1 + fmaf(y1[j], Q[j], R[j]);
+    }
+    Vec<T, VEC>::store(dy + v0 * ldd + c0, g0);
+    Vec<T, VEC>::store(dy + v1 * ldd + c0, g1);
+  }
+  if (vi < V) {
+    const long long vox = nb + vi;
     float yv[VEC], gv[VEC], o[VEC];
     Vec<T, VEC>::load(y + vox * ldy + c0, yv);
     Vec<T, VEC>::load(g + vox * ldg + c0, gv);
@@ -847,10 +962,10 @@ static bool vec_ok(const b200seg_tensor* t) {
 }
 
 // blocks per sample such that gridDim.x*256 is a multiple of G and the grid fills the chip
-static int ew_blocks(long long V, int G, int N, int device) {
+static int ew_blocks(long long V, int G, int N, int device, int per_sm = 8) {
   long long total = V * G;
   long long want = (total + 256 * 4 - 1) / (256 * 4);        // ~4 groups per thread
-  long long cap = ((long long)num_sms(device) * 8 + N - 1) / N;
+  long long cap = ((long long)num_sms(device) * per_sm + N - 1) / N;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   // 256 % G == 0 for every power-of-two G <= 256; otherwise round blocks so that blocks*256 % G == 0
@@ -930,7 +1045,7 @@ int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, co
   const int C = out->c;
   EW_DISPATCH(out, vok, {
     const int G = C / VEC;
-    dim3 grid(ew_blocks(V, G, out->n, device), out->n);
+    dim3 grid(ew_blocks(V, G, out->n, device, 3), out->n);
     const int mg = (g1 && g2 && g2->groups > g1->groups) ? g2->groups : (g1 ? g1->groups : 1);
     const size_t smem = gn_cta_doubles(C, mg, false) * sizeof(double) + (size_t)7 * C * sizeof(float);
     apply_kernel<T, VEC><<<grid, 256, smem, s>>>(
@@ -950,20 +1065,12 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
   const int C = y->c;
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
-    dim3 grid(ew_blocks(V, G, y->n, device), y->n);
+    dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
     const bool pow2g = (G & (G - 1)) == 0;
     const int groups = (gn && gn->stats) ? gn->groups : 1;
     const size_t base = (3 * C + gn_cta_doubles(C, groups, false)) * sizeof(double) + (size_t)5 * C * sizeof(float);
-    const size_t staged_bytes = base + (size_t)8 * 3 * C * sizeof(double);
-    const int staged = (pow2g && G <= 32 && staged_bytes <= 96 * 1024) ? 1 : 0;
-    if (staged && staged_bytes > 48 * 1024) {
-      static int attr_done[64] = {0};                      // per device, per instantiation
-      if (device >= 0 && device < 64 && !attr_done[device]) {
-        B200_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       96 * 1024));
-        attr_done[device] = 1;
-      }
-    }
+    const size_t staged_bytes = base + (size_t)8 * 3 * C * sizeof(float);
+    const int staged = (pow2g && G <= 32 && staged_bytes <= 46 * 1024) ? 1 : 0;
     gn_bwd_reduce_kernel<T, VEC><<<grid, 256, staged ? staged_bytes : base, s>>>(
         static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
         make_gnref(gn, C), staged);
@@ -994,7 +1101,7 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
   B200_CHECK_ARG(!(gn && gn->stats) || C <= 512, "gn_bwd_apply: fused coefficients support C <= 512 (got %d)", C);
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
-    dim3 grid(ew_blocks(V, G, y->n, device), y->n);
+    dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
     const int groups = (gn && gn->stats) ? gn->groups : 1;
     const size_t smem = gn_cta_doubles(C, groups, true) * sizeof(double) + (size_t)8 * C * sizeof(float);
     gn_bwd_apply_kernel<T, VEC><<<grid, 256, smem, s>>>(static_cast<const T*>(g->ptr), g->ld,

@@ -30,8 +30,9 @@ class Timer:
     figure interleaves a 256 MiB write before every call and subtracts a graph holding only the writes."""
     INNER = 10
 
-    def __init__(self, reps):
+    def __init__(self, reps, eager=False):
         self.reps = reps
+        self.eager = eager
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
         self.rows = []
         self.flush_us = None
@@ -62,6 +63,12 @@ class Timer:
         return ts[len(ts) // 2]
 
     def run(self, name, fn, bytes_=0, flops=0):
+        if self.eager:                 # for ncu: two plain launches per op, no graphs, no timing
+            fn()
+            fn()
+            torch.cuda.synchronize()
+            print("ran", name, flush=True)
+            return
         if self.flush_us is None:
             def only_flush():
                 for _ in range(self.INNER):
@@ -191,9 +198,10 @@ def main():
     ap.add_argument("--only", default="stem,gn,pack,wgrad,conv")
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--tag", default="run")
+    ap.add_argument("--eager", action="store_true", help="launch every op twice without graphs/timing (ncu runs)")
     a = ap.parse_args()
     be = CudaBackend()
-    tm = Timer(a.reps)
+    tm = Timer(a.reps, a.eager)
     which = set(a.only.split(","))
     with torch.no_grad():
         if "stem" in which:
