@@ -37,6 +37,8 @@ extern "C" {
 #define B200SEG_BF16 1
 #define B200SEG_BF16_TC 2 /* weights only: bf16 packed [tap][N][K] (K-major) for the tcgen05/TMA conv path */
 #define B200SEG_BF16_HALO 3 /* weights only: bf16 packed [tap][K/8][N][8] (smem image of the halo-staged 3x3x3 path) */
+#define B200SEG_BF16_HALO_WS 4 /* weights only: bf16 packed [N/NT][tap][K/8][NT][8], NT = b200seg_conv_halo_ws_ntile():
+                                  per-group tap blocks streamed by the 64/128-channel halo-staged 3x3x3 path */
 
 /* conv kinds */
 #define B200SEG_K3 0    /* 3x3x3 (dims==3) or 1x3x3 (dims==2), stride 1, zero pad 1 */
@@ -109,6 +111,9 @@ int b200seg_conv_tc_eligible(int kind, int cin, int cout);
  * B200SEG_BF16_HALO weights; meant for the full-resolution layers (each input voxel is staged once in shared
  * memory instead of once per tap). */
 int b200seg_conv_halo_eligible(int kind, int cin, int cout);
+/* columns per weight group (NT) if (kind, Cin -> Cout) can run on the weight-streaming halo-staged tcgen05 kernel
+ * (3x3x3, 64/128 input channels: the 24^3 / 12^3 pyramid levels) given B200SEG_BF16_HALO_WS weights, else 0. */
+int b200seg_conv_halo_ws_ntile(int kind, int cin, int cout);
 
 /* weight-gradient half of aten::convolution_backward:
  *   dwp[t][ka][kb] += sum_{n,o} a[n, o*s + t - p, ka] * b[n, o, kb]      (fp32, caller zero-fills)

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 K3, K1, DOWN, UP = 0, 1, 2, 3
-F32, BF16, BF16_TC, BF16_HALO = 0, 1, 2, 3
+F32, BF16, BF16_TC, BF16_HALO, BF16_HALO_WS = 0, 1, 2, 3, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200seg.so")
@@ -51,6 +51,7 @@ _SIGNATURES = {
     "b200seg_conv": ([_i, _i, _PT, _vp, _i, _vp, _PT, _vp, _PT, _i, _vp], C.c_int),
     "b200seg_conv_tc_eligible": ([_i, _i, _i], C.c_int),
     "b200seg_conv_halo_eligible": ([_i, _i, _i], C.c_int),
+    "b200seg_conv_halo_ws_ntile": ([_i, _i, _i], C.c_int),
     "b200seg_wgrad": ([_i, _i, _PT, _PT, _vp, _i, _vp], C.c_int),
     "b200seg_gn_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_apply": ([_PT, _vp, _PT, _vp, _PT, _PT, _i, _vp], C.c_int),
@@ -158,6 +159,8 @@ class CudaBackend:
         self.use_tc = os.environ.get("B200SEG_DISABLE_TC", "0") != "1"
         self.use_halo = os.environ.get("B200SEG_DISABLE_HALO", "0") != "1"
         self.halo_min_vox = int(os.environ.get("B200SEG_HALO_MIN_VOX", str(128 * 128)))
+        self.use_halo_ws = os.environ.get("B200SEG_DISABLE_HALO_WS", "0") != "1"
+        self.halo_ws_min_vox = int(os.environ.get("B200SEG_HALO_WS_MIN_VOX", "1000"))
         self._pinned_forever, self._pinned_ring, self._keep_tables = [], [], []
         self.launch_count = 0      # kernels launched through the C ABI (one per successful entry-point call)
 
@@ -177,10 +180,22 @@ class CudaBackend:
 
     # ------------------------------------------------------------------ weights
     def _pack_plan(self, w, kind, which, dtype, dims, allow_tc=True, vox=None):
-        """-> (out_shape, layout code, (T, K, N2, N1, st, sk, sn2, sn1, flip)) for one conv operand."""
+        """-> (out_shape, layout code, (T, K, N2, N1, st, sk, sn2, sn1, flip)) for one conv operand; for the
+        grouped layout the last element is a LIST of (src element offset, dst element offset, args) parts."""
         a, b = w.shape[0], w.shape[1]
         t = w.numel() // (a * b)
         od = F32 if dtype == torch.float32 else BF16
+        if (allow_tc and self.use_tc and self.use_halo_ws and dtype == torch.bfloat16 and kind == K3 and dims == 3
+                and vox is not None and vox >= self.halo_ws_min_vox):
+            cin, cout = (b, a) if which == "fwd" else (a, b)
+            nt = self.lib.b200seg_conv_halo_ws_ntile(kind, cin, cout)
+            if nt > 0:
+                g = cout // nt
+                if which == "fwd":      # [co/NT][t][ci/8][co%NT][ci%8]
+                    parts = [(i * nt * b * t, i * t * b * nt, (t, b // 8, nt, 8, 1, 8 * t, b * t, t, 0)) for i in range(g)]
+                else:                   # [ci/NT][T-1-t][co/8][ci%NT][co%8]
+                    parts = [(i * nt * t, i * t * a * nt, (t, a // 8, nt, 8, 1, 8 * b * t, t, b * t, 1)) for i in range(g)]
+                return (g, t, cin // 8, nt, 8), BF16_HALO_WS, parts
         if (allow_tc and self.use_tc and self.use_halo and dtype == torch.bfloat16 and kind == K3
                 and vox is not None and vox >= self.halo_min_vox):
             cin, cout = (b, a) if which == "fwd" else (a, b)
@@ -221,9 +236,11 @@ class CudaBackend:
         shape, code, args = self._pack_plan(w, kind, which, dtype, dims, allow_tc, vox)
         out = torch.empty(shape, dtype=dtype, device=w.device)
         od = F32 if dtype == torch.float32 else BF16
-        T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
-        self._check(self.lib.b200seg_pack_weight(w.data_ptr(), out.data_ptr(), od, T, K, N2, N1, s_t, s_k, s_n2, s_n1,
-                                                 flip, dev, st))
+        parts = args if isinstance(args, list) else [(0, 0, args)]
+        for so, do, (T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip) in parts:
+            self._check(self.lib.b200seg_pack_weight(w.data_ptr() + so * w.element_size(),
+                                                     out.data_ptr() + do * out.element_size(), od, T, K, N2, N1,
+                                                     s_t, s_k, s_n2, s_n1, flip, dev, st))
         return PackedWeight(out, code, w, kind, which, dims)
 
     def _table_to_device(self, descs, device):
@@ -251,11 +268,13 @@ class CudaBackend:
         for (w, kind, which, dtype, dims, vox) in reqs:
             shape, code, args = self._pack_plan(w, kind, which, dtype, dims, True, vox)
             out = torch.empty(shape, dtype=dtype, device=w.device)
-            T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip = args
-            nb = max(1, min(256, (out.numel() + 4095) // 4096))
-            descs.append(PackDesc(w.data_ptr(), out.data_ptr(), s_t, s_k, s_n2, s_n1,
-                                  F32 if dtype == torch.float32 else BF16, T, K, N2, N1, flip, blocks, nb))
-            blocks += nb
+            parts = args if isinstance(args, list) else [(0, 0, args)]
+            for so, do, (T, K, N2, N1, s_t, s_k, s_n2, s_n1, flip) in parts:
+                nb = max(1, min(256, (T * K * N2 * N1 + 4095) // 4096))
+                descs.append(PackDesc(w.data_ptr() + so * w.element_size(), out.data_ptr() + do * out.element_size(),
+                                      s_t, s_k, s_n2, s_n1, F32 if dtype == torch.float32 else BF16, T, K, N2, N1,
+                                      flip, blocks, nb))
+                blocks += nb
             outs.append(PackedWeight(out, code, w, kind, which, dims))
         table = self._table_to_device(descs, reqs[0][0].device)
         self._check(self.lib.b200seg_pack_weights_multi(table.data_ptr(), len(descs), blocks, dev, st))
@@ -288,7 +307,7 @@ class CudaBackend:
     # ------------------------------------------------------------------ conv family
     def conv(self, kind, dims, x, wpk, bias, y, stats, addend):
         dev, st = self._ds(x)
-        if wpk.code in (BF16_TC, BF16_HALO) and not (x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16):
+        if wpk.code in (BF16_TC, BF16_HALO, BF16_HALO_WS) and not (x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16):
             # tcgen05 path needs bf16 activations on both sides (e.g. a 16-channel fp32 network input)
             wpk = self.pack_weight(wpk.src, wpk.kind, wpk.which, torch.bfloat16, wpk.dims, allow_tc=False)
         dx, dy, da = _desc(x), _desc(y), _desc(addend)

@@ -29,6 +29,11 @@ int conv_halo_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype
                         const b200seg_tensor* addend);
 int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
               double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
+int conv_halows_ntile(int kind, int cin, int cout);
+int conv_halows_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                          const b200seg_tensor* addend);
+int conv_halows(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias,
+                const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
 int conv_tc_channels_ok(int kind, int cin, int cout);
 int smallcin_conv_supported(int kind, const b200seg_tensor* x, const b200seg_tensor* y, const b200seg_tensor* addend);
 int smallcin_conv(int kind, int dims, const b200seg_tensor* x, const void* w, int w_dtype, const float* bias,
@@ -158,7 +163,11 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
     if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
     return conv_halo(kind, dims, x, wpk, bias, y, stats, addend, device, ST(stream));
   }
-  B200_CHECK_ARG(w_dtype != B200SEG_BF16_TC && w_dtype != B200SEG_BF16_HALO,
+  if (conv_halows_supported(kind, dims, x, w_dtype, y, addend)) {
+    if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
+    return conv_halows(kind, dims, x, wpk, bias, y, stats, addend, device, ST(stream));
+  }
+  B200_CHECK_ARG(w_dtype != B200SEG_BF16_TC && w_dtype != B200SEG_BF16_HALO && w_dtype != B200SEG_BF16_HALO_WS,
                  "b200seg_conv: B200SEG_BF16_TC weights need bf16, 16-byte aligned activations of a supported shape");
   static const bool stem_off = [] {
     const char* e = getenv("B200SEG_DISABLE_STEM");
@@ -178,6 +187,8 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
 int b200seg_conv_tc_eligible(int kind, int cin, int cout) { return conv_tc_channels_ok(kind, cin, cout); }
 
 int b200seg_conv_halo_eligible(int kind, int cin, int cout) { return conv_halo_channels_ok(kind, cin, cout); }
+
+int b200seg_conv_halo_ws_ntile(int kind, int cin, int cout) { return conv_halows_ntile(kind, cin, cout); }
 
 int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
                   b200seg_stream stream) {

@@ -250,3 +250,49 @@ def test_halo_conv_matches_emulation(be, dims, n, sp, cin, cout, which):
         assert float(ybuf[..., :16].abs().max()) == 0 and float(ybuf[..., 16 + co:].abs().max()) == 0
         if with_stats:
             assert rel(st_c, st_e) < 1e-4
+
+
+HALO_WS_CASES = [
+    # n, spatial, cin, cout
+    (2, (24, 24, 24), 64, 64),            # the VNet level (6 column tiles, 6 d-chunks of 4, 2 channel groups)
+    (1, (6, 16, 8), 64, 64),              # one column, ragged d chunk (6 = 4 + 2)
+    (1, (5, 20, 12), 64, 64),             # tile overhang in h and w, one channel group
+    (2, (12, 12, 12), 128, 128),          # the 12^3 level: 2-slice items, 4 channel groups
+    (1, (3, 8, 8), 128, 64),              # one-slice items
+    (1, (7, 16, 16), 64, 128),            # more items than fit one pass per CTA is not needed; 4 groups
+]
+
+
+@pytest.mark.parametrize("n,sp,cin,cout", HALO_WS_CASES)
+@pytest.mark.parametrize("which", ["fwd", "dgrad"])
+def test_halo_ws_conv_matches_emulation(be, n, sp, cin, cout, which):
+    """weight-streaming halo kernel (64/128 input channels) against the emulated conv"""
+    g = torch.Generator().manual_seed(17)
+    dt = torch.bfloat16
+    w = torch.randn((cout, cin, 3, 3, 3), generator=g) * (2.0 / (cin * 27)) ** 0.5
+    ci, co = (cin, cout) if which == "fwd" else (cout, cin)
+    if ci not in (64, 128):
+        pytest.skip("data-gradient form has an input channel count the kernel does not take")
+    bias = torch.randn(co, generator=g) * 0.1
+    xbuf = torch.randn((n,) + sp + (ci + 16,), generator=g).to(dt)
+    x = xbuf[..., 8:8 + ci]
+    wp_c = be.pack_weight(w.cuda(), K3, which, dt, 3, vox=10 ** 9)
+    assert wp_c.code == 4, "expected the grouped weight-streaming layout"
+    wp_e = EMU.pack_weight(w, K3, which, dt, 3)
+    many = be.pack_many([(w.cuda(), K3, which, dt, 3, 10 ** 9)])[0]
+    torch.cuda.synchronize()
+    assert many.code == 4 and torch.equal(many.t, wp_c.t)
+    for with_stats, with_addend in ((True, False), (False, True)):
+        y_e = torch.zeros((n,) + sp + (co,), dtype=dt)
+        ybuf = torch.zeros((n,) + sp + (co + 32,), dtype=dt, device="cuda")
+        y_c = ybuf[..., 16:16 + co]
+        st_e = torch.zeros(n, co, 2, dtype=torch.float64) if with_stats else None
+        st_c = st_e.clone().cuda() if with_stats else None
+        add = torch.randn((n,) + sp + (co,), generator=g).to(dt) if with_addend else None
+        EMU.conv(K3, 3, x, wp_e, bias, y_e, st_e, add)
+        be.conv(K3, 3, x.cuda(), wp_c, bias.cuda(), y_c, st_c, add.cuda() if with_addend else None)
+        torch.cuda.synchronize()
+        assert rel(y_c, y_e) < 6e-3, rel(y_c, y_e)
+        assert float(ybuf[..., :16].abs().max()) == 0 and float(ybuf[..., 16 + co:].abs().max()) == 0
+        if with_stats:
+            assert rel(st_c, st_e) < 1e-4
