@@ -167,8 +167,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 class TimedBackend:
     TIMED = ("conv", "wgrad", "apply", "gn_bwd_reduce", "gn_bwd_apply", "gn_finalize", "gn_bwd_finalize",
-             "pack_weight", "unpack_wgrad", "colsum", "head_probs", "loss_partials", "loss_finalize", "loss_bwd",
-             "pool_fwd", "pool_bwd")
+             "apply_gn", "gn_bwd_reduce_gn", "gn_bwd_apply_gn", "pack_weight", "unpack_wgrad", "colsum",
+             "head_probs", "head_fwd", "head_bwd", "loss_partials", "loss_finalize", "loss_bwd", "pool_fwd",
+             "pool_bwd")       # (pack_many / unpack_many build their descriptor tables on the host: not event-timed here)
 
     def __init__(self, inner):
         self.inner, self.records = inner, []
@@ -191,7 +192,9 @@ class TimedBackend:
     def _describe(name, a):
         if name == "conv":
             kind, dims, x, wpk, bias, y = a[:6]
-            path = {2: "/tcgen05", 3: "/tcgen05-halo"}.get(getattr(wpk, "code", 0), "/cuda-core")
+            path = {2: "/tcgen05", 3: "/tcgen05-halo", 4: "/tcgen05-halo-ws"}.get(getattr(wpk, "code", 0), "/cuda-core")
+            if x.shape[-1] == 1 and y.dtype == torch.bfloat16:
+                path = "/mma.sync-stem"
             return f"conv[k{kind}{path}] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
         if name == "wgrad":
             kind, dims, x, dy = a[:4]
@@ -475,7 +478,13 @@ def main():
                     "frac": tc_frac}
         else:
             roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
-        roof.update({"kernel": desc, "launches_per_step": d["n"], "avg_us": dur * 1e6, "traffic": None,
+        traffic = None                # DRAM bytes per launch from the committed ncu --set full capture, if this
+        try:                          # kernel/shape was captured (profiles/ncu_traffic.json)
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(desc, {}).get("dram_bytes")
+        except OSError:
+            pass
+        roof.update({"kernel": desc, "launches_per_step": d["n"], "avg_us": dur * 1e6, "traffic": traffic,
                      "peaks": peaks["source"],
                      "share_of_step": d["ms"] / max(1e-9, sum(v["ms"] for v in kern.values()))})
         ranked_all = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])
