@@ -15,6 +15,8 @@
 // A CTA owns a contiguous chunk of voxel tiles and up to 512/kb accumulator blocks (128 rows each)
 // resident in TMEM for its whole lifetime; the epilogue adds them into dwp with vectorised fp32 atomics
 // (split-K over the grid).  Warp roles as in conv_tc.cu.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace b200seg {
@@ -251,8 +253,49 @@ int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* 
   p.CA = sub_channels(p.Ka);
   p.CB = sub_channels(p.Kb);
   p.mblocks_total = (p.Rtot + 127) / 128;
-  p.mb_per_cta = 512 / p.Kb;
-  if (p.mb_per_cta > p.mblocks_total) p.mb_per_cta = p.mblocks_total;
+  // Decomposition: grid.y = groups of accumulator blocks (128 rows of (tap, ka) each), grid.x = split-K over the
+  // voxel tiles.  Every K split adds its partial dW with fp32 atomics, i.e. grid.x * |dW| bytes of L2 atomic traffic:
+  // at the small pyramid levels (few voxel tiles, large dW) that flush, not the K loop, is the run time.  The B tile
+  // is re-loaded per accumulator block anyway, so fewer blocks per CTA (more groups, fewer K splits) costs nothing
+  // in the loop.  Pick the block count per CTA that minimises  stages * t_stage + flush / rate.
+  const int sms_ = num_sms(device);
+  const int max_mb = (512 / p.Kb) < p.mblocks_total ? (512 / p.Kb) : p.mblocks_total;
+  {
+    const double stage_bytes = 128.0 * 128.0 * 2.0 + 128.0 * p.Kb * 2.0;
+    const double stage_rows = 128.0 * (128 / p.CA) + 128.0 * (p.Kb / p.CB);             // TMA rows per stage
+    double t_stage = stage_bytes / 88e3;                                                // us: ~88 GB/s ingest per SM
+    if (t_stage < stage_rows * 1.06e-3) t_stage = stage_rows * 1.06e-3;                 // ~1 row/ns for short rows
+    const double dw_bytes = (double)p.Rtot * p.Kb * 4.0;
+    const double last_w = (double)(p.Rtot - 128 * (p.mblocks_total - 1)) / 128.0;       // the last block may be partial
+    auto estimate = [&](int mb) {
+      const int gy_ = (p.mblocks_total + mb - 1) / mb;
+      int gx_ = sms_ / gy_;
+      if (gx_ < 1) gx_ = 1;
+      if (gx_ > p.ntiles) gx_ = p.ntiles;
+      const int mbc = (p.mblocks_total + gy_ - 1) / gy_;
+      // heaviest row group (the last block of the last group may be partial)
+      const double heavy = gy_ == 1 ? (double)(mbc - 1) + last_w : (double)mbc;
+      const double stages = (double)((p.ntiles + gx_ - 1) / gx_) * heavy;
+      const double waves = gy_ > sms_ ? (double)((gy_ + sms_ - 1) / sms_) : 1.0;
+      return waves * stages * t_stage + gx_ * dw_bytes / 1.5e6;                          // us: ~1.5 TB/s of atomics
+    };
+    // default: as many accumulator blocks per CTA as TMEM holds (fewest CTAs touching a tile); switch only for a
+    // clear predicted gain (the model is calibrated on the VNet3d layer shapes, tools/microbench_ops.py)
+    int best_mb = max_mb;
+    double best = estimate(max_mb) * 0.85;
+    for (int mb = 1; mb < max_mb; ++mb) {
+      const double t = estimate(mb);
+      if (t < best - 1e-9) {
+        best = t;
+        best_mb = mb;
+      }
+    }
+    static const int forced = [] {
+      const char* e = getenv("B200SEG_WGRAD_MB");
+      return e ? atoi(e) : 0;
+    }();
+    p.mb_per_cta = forced > 0 ? (forced < max_mb ? forced : max_mb) : best_mb;
+  }
   const int gy = (p.mblocks_total + p.mb_per_cta - 1) / p.mb_per_cta;
   // balance the accumulator blocks over the row groups
   p.mb_per_cta = (p.mblocks_total + gy - 1) / gy;
