@@ -59,6 +59,9 @@ int head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* 
 int head_bwd_supported(const b200seg_tensor* x, int nc);
 int head_bwd(const b200seg_tensor* x, const float* dl, const float* w, const b200seg_tensor* dx, float* dw, float* db,
              int nc, int device, cudaStream_t st);
+int wgrad_halo_mma_supported(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b);
+int wgrad_halo_mma(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
+                   cudaStream_t st);
 int wgrad_tc_supported(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b);
 int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* b, float* dwp, int device,
              cudaStream_t st);
@@ -202,6 +205,8 @@ int b200seg_wgrad(int kind, int dims, const b200seg_tensor* a, const b200seg_ten
     const char* e2 = getenv("B200SEG_DISABLE_TC");
     return (e && e[0] == '1') || (e2 && e2[0] == '1');
   }();
+  if (!tc_off && wgrad_halo_mma_supported(kind, dims, a, b))
+    return wgrad_halo_mma(kind, dims, a, b, dwp, device, ST(stream));
   if (!tc_off && wgrad_tc_supported(kind, dims, a, b)) {
     if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
     return wgrad_tc(kind, dims, a, b, dwp, device, ST(stream));

@@ -114,6 +114,12 @@ WG_CASES = [
     (K1, 3, 2, (8, 8, 8), 32, 16),
     (K1, 3, 1, (4, 12, 12), 256, 128),
     (K3, 3, 2, (24, 24, 24), 32, 32),     # more voxel tiles than one CTA chunk
+    # >= 32768 voxels per sample with 16/32 channels: the halo-tile mma.sync weight gradient (wgrad_halo_mma.cu)
+    (K3, 3, 1, (32, 32, 32), 16, 16),     # W % 32 == 0: 32-wide tiles
+    (K3, 3, 2, (24, 40, 48), 16, 16),     # 16-wide tiles, several tiles per CTA, two samples
+    (K3, 3, 1, (32, 32, 32), 32, 32),     # one (kd, kh) tap row per warp
+    (K3, 3, 1, (16, 48, 48), 32, 16),
+    (K3, 3, 1, (16, 48, 64), 16, 32),
 ]
 
 
