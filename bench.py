@@ -195,6 +195,9 @@ class TimedBackend:
             path = {2: "/tcgen05", 3: "/tcgen05-halo", 4: "/tcgen05-halo-ws"}.get(getattr(wpk, "code", 0), "/cuda-core")
             if x.shape[-1] == 1 and y.dtype == torch.bfloat16:
                 path = "/mma.sync-stem"
+            elif (kind in (1, 3) and getattr(wpk, "code", 0) == 2 and max(x.shape[-1], y.shape[-1]) <= 64
+                  and y.numel() // y.shape[-1] >= 65536 and x.shape[-1] * y.shape[-1] <= (512 if kind == 3 else 2048)):
+                path = "/mma.sync-pointwise"      # pw_mma.cu takes these shapes ahead of the tcgen05 kernel
             return f"conv[k{kind}{path}] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
         if name == "wgrad":
             kind, dims, x, dy = a[:4]

@@ -29,6 +29,10 @@ int conv_halo_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype
                         const b200seg_tensor* addend);
 int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
               double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
+int pw_mma_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                     const b200seg_tensor* addend);
+int pw_mma_conv(int kind, int dims, const b200seg_tensor* x, const void* w, const float* bias,
+                const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
 int conv_halows_ntile(int kind, int cin, int cout);
 int conv_halows_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
                           const b200seg_tensor* addend);
@@ -160,6 +164,8 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
   B200_CHECK_ARG(dims == 2 || dims == 3, "b200seg_conv: dims must be 2 or 3");
   B200_CHECK_ARG(dims == 3 || (x->d == 1 && y->d == 1), "b200seg_conv: 2-D tensors must have d == 1");
   B200_DEVICE(device);
+  if (pw_mma_supported(kind, dims, x, w_dtype, y, addend))
+    return pw_mma_conv(kind, dims, x, wpk, bias, y, stats, addend, device, ST(stream));
   if (conv_tc_supported(kind, dims, x, w_dtype, y, addend))
     return conv_tc(kind, dims, x, wpk, bias, y, stats, addend, device, ST(stream));
   if (conv_halo_supported(kind, dims, x, w_dtype, y, addend)) {

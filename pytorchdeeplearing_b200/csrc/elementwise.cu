@@ -78,6 +78,7 @@ __device__ __forceinline__ int pack_find_desc(const PackDesc* __restrict__ table
 
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int count) {
   __shared__ float s_tile[kPackMaxT][kPackCols + 1];
+  __shared__ long long s_col[kPackCols];
   __shared__ int s_start[1024];
   const PackDesc d = table[pack_find_desc(table, count, s_start)];
   const int b = blockIdx.x - d.block_start;
@@ -92,20 +93,23 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
     const int sc = lane / T, ts = lane - sc * T;
     for (int j0 = b * kPackCols; j0 < J; j0 += d.nblocks * kPackCols) {
       const int ncol = J - j0 < kPackCols ? J - j0 : kPackCols;
+      // source offset of every column of the tile: decoded once per column (the divisions), not once per element
+      if ((int)threadIdx.x < ncol) {
+        const int j = j0 + threadIdx.x;
+        const int n1 = j % d.N1;
+        const int r = j / d.N1;
+        const int n2 = r % d.N2;
+        const int k = r / d.N2;
+        s_col[threadIdx.x] = k * d.sk + n2 * d.sn2 + n1 * d.sn1;
+      }
+      __syncthreads();
       // all of a warp's column trips are loaded before the first shared-memory store (one latency, not eight)
       float v[kPackIters];
 #pragma unroll
       for (int i = 0; i < kPackIters; ++i) {
         const int jl = warp * cpw + sc + i * 8 * cpw;
         v[i] = 0.f;
-        if (sc < cpw && jl < ncol) {
-          const int j = j0 + jl;
-          const int n1 = j % d.N1;
-          const int r = j / d.N1;
-          const int n2 = r % d.N2;
-          const int k = r / d.N2;
-          v[i] = d.src[ts + k * d.sk + n2 * d.sn2 + n1 * d.sn1];
-        }
+        if (sc < cpw && jl < ncol) v[i] = d.src[ts + s_col[jl]];
       }
 #pragma unroll
       for (int i = 0; i < kPackIters; ++i) {
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
 // unpack: dst[t*st + k*sk + n*sn2] = src[(t*K + k)*N2 + n]   (N1 unused = 1)
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __restrict__ table, int count) {
   __shared__ float s_tile[kPackMaxT][kPackCols + 1];
+  __shared__ long long s_col[kPackCols];
   __shared__ int s_start[1024];
   const PackDesc d = table[pack_find_desc(table, count, s_start)];
   const int b = blockIdx.x - d.block_start;
@@ -184,15 +189,13 @@ __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __res
           s_tile[t][jl] = d.src[(long long)t * J + j0 + jl];
         }
       }
-      __syncthreads();
-      for (int jl = warp * cpw + sc; jl < ncol; jl += 8 * cpw) {
-        if (sc < cpw) {
-          const int j = j0 + jl;
-          const int n = j % d.N2;
-          const int k = j / d.N2;
-          out[ts + k * d.sk + n * d.sn2] = s_tile[ts][jl];
-        }
+      if ((int)threadIdx.x < ncol) {
+        const int j = j0 + threadIdx.x;
+        s_col[threadIdx.x] = (j / d.N2) * d.sk + (j % d.N2) * d.sn2;
       }
+      __syncthreads();
+      for (int jl = warp * cpw + sc; jl < ncol; jl += 8 * cpw)
+        if (sc < cpw) out[ts + s_col[jl]] = s_tile[ts][jl];
       __syncthreads();
     }
     return;

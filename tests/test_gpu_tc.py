@@ -37,6 +37,11 @@ TC_CASES = [
     (K1, 3, 2, (8, 8, 8), 32, 16),
     (K1, 3, 1, (4, 12, 12), 256, 128),
     (K1, 2, 2, (1, 16, 16), 64, 32),
+    # >= 65536 voxels: the register-level mma.sync pointwise kernel (pw_mma.cu)
+    (K1, 3, 2, (32, 32, 32), 32, 16),
+    (K1, 3, 1, (32, 32, 64), 16, 32),
+    (K1, 3, 3, (16, 32, 64), 64, 32),     # three samples: statistics flushed per sample
+    (K1, 2, 1, (1, 256, 256), 32, 32),
 ]
 
 
@@ -156,6 +161,10 @@ RESAMPLE_CASES = [
     (UP, 3, 2, (6, 6, 6), 64, 32),            # ragged
     (UP, 2, 2, (1, 16, 24), 32, 16),
     (UP, 2, 1, (1, 8, 8), 256, 128),
+    # fine volume >= 65536 voxels, Cin*Cout <= 512: the register-level mma.sync transposed conv (pw_mma.cu)
+    (UP, 3, 2, (16, 16, 32), 32, 16),
+    (UP, 3, 1, (8, 32, 32), 16, 32),
+    (UP, 2, 1, (1, 128, 128), 32, 16),
 ]
 
 
