@@ -150,6 +150,15 @@ int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, co
                             const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int device,
                             b200seg_stream stream);
 
+/* b200seg_gn_bwd_reduce_gn + b200seg_gn_bwd_apply_gn in ONE launch for small tensors (the 24^3 level and below: the
+ * two passes are separated by a grid-wide barrier and the tensors stay in L2).  `sums` [N][C][3] and the barrier
+ * word `counter` must be zero on entry; every CTA of the launch has to be resident, so ask
+ * b200seg_gn_bwd_fused_supported (size, layout, N <= #SMs) first and fall back to the two-launch form. */
+int b200seg_gn_bwd_fused_supported(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_tensor* dy, int device);
+int b200seg_gn_bwd_fused_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
+                            unsigned int* counter, const b200seg_tensor* dy, float* dgamma, float* dbeta,
+                            float* dbias, int device, b200seg_stream stream);
+
 /* native_group_norm_backward + threshold_backward + dropout backward:
  *   sums[n][c] += { sum g*m, sum g*m*y, sum y },  m = [y*A+B > 0] */
 int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums,

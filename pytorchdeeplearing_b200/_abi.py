@@ -58,6 +58,8 @@ _SIGNATURES = {
     "b200seg_apply_gn": ([_PT, _PG, _PT, _PG, _PT, _PT, _i, _vp], C.c_int),
     "b200seg_gn_bwd_reduce_gn": ([_PT, _PT, _PG, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_apply_gn": ([_PT, _PT, _PG, _vp, _PT, _vp, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_fused_supported": ([_PT, _PT, _PT, _i], C.c_int),
+    "b200seg_gn_bwd_fused_gn": ([_PT, _PT, _PG, _vp, _vp, _PT, _vp, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_reduce": ([_PT, _PT, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_finalize": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_apply": ([_PT, _PT, _vp, _vp, _PT, _i, _vp], C.c_int),
@@ -359,6 +361,23 @@ class CudaBackend:
         self._check(self.lib.b200seg_gn_bwd_apply_gn(C.byref(dg), C.byref(dyy), C.byref(gg), sums.data_ptr(),
                                                      C.byref(dd), dgamma.data_ptr(), dbeta.data_ptr(), _p(dbias),
                                                      dev, st))
+
+    fused_gn_bwd = os.environ.get("B200SEG_FUSED_GN_BWD", "1") != "0"
+
+    def gn_bwd_fused_ok(self, g, y, dy):
+        if not (self.fused_gn and self.fused_gn_bwd):
+            return False
+        dev, _ = self._ds(y)
+        dg, dyy, dd = _desc(g), _desc(y), _desc(dy)
+        return bool(self.lib.b200seg_gn_bwd_fused_supported(C.byref(dg), C.byref(dyy), C.byref(dd), dev))
+
+    def gn_bwd_fused_gn(self, g, y, gn, sums, counter, dy, dgamma, dbeta, dbias):
+        """sums [N][C][3] fp64 and counter (>= 4 bytes) zero on entry; one launch instead of reduce + apply"""
+        dev, st = self._ds(y)
+        dg, dyy, dd, gg = _desc(g), _desc(y), _desc(dy), self._gn(gn)
+        self._check(self.lib.b200seg_gn_bwd_fused_gn(C.byref(dg), C.byref(dyy), C.byref(gg), sums.data_ptr(),
+                                                     counter.data_ptr(), C.byref(dd), dgamma.data_ptr(),
+                                                     dbeta.data_ptr(), _p(dbias), dev, st))
 
     def gn_bwd_reduce(self, g, y, coef, sums):
         dev, st = self._ds(y)

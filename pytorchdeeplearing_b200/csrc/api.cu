@@ -86,6 +86,10 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
 int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, const float* scale, int N, int C,
                        int groups, long long vox, float* coef3, float* dgamma, float* dbeta, float* dbias,
                        cudaStream_t s);
+int ew_gn_bwd_fused_supported(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_tensor* dy);
+int ew_gn_bwd_fused(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
+                    unsigned int* counter, float* dgamma, float* dbeta, float* dbias, const b200seg_tensor* dy,
+                    int device, cudaStream_t s);
 int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
                     const b200seg_gn* gn, const double* sums, float* dgamma, float* dbeta, float* dbias,
                     const b200seg_tensor* dy, int device, cudaStream_t s);
@@ -281,6 +285,24 @@ int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, co
   B200_CHECK_ARG(valid_gn(gn, y->c) && sums && dgamma && dbeta, "b200seg_gn_bwd_apply_gn: bad argument");
   B200_DEVICE(device);
   return ew_gn_bwd_apply(g, y, nullptr, nullptr, gn, sums, dgamma, dbeta, dbias, dy, device, ST(stream));
+}
+
+int b200seg_gn_bwd_fused_supported(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_tensor* dy,
+                                   int device) {
+  if (g == nullptr || y == nullptr || dy == nullptr) return 0;
+  if (!ew_gn_bwd_fused_supported(g, y, dy)) return 0;
+  return y->n <= num_sms(device) ? 1 : 0;
+}
+
+int b200seg_gn_bwd_fused_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
+                            unsigned int* counter, const b200seg_tensor* dy, float* dgamma, float* dbeta,
+                            float* dbias, int device, b200seg_stream stream) {
+  REQ_TENSOR(g, "g");
+  REQ_TENSOR(y, "y");
+  REQ_TENSOR(dy, "dy");
+  B200_CHECK_ARG(valid_gn(gn, y->c) && sums && counter && dgamma && dbeta, "b200seg_gn_bwd_fused_gn: bad argument");
+  B200_DEVICE(device);
+  return ew_gn_bwd_fused(g, y, gn, sums, counter, dgamma, dbeta, dbias, dy, device, ST(stream));
 }
 
 int b200seg_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, double* sums, int device,

@@ -810,6 +810,134 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const T* __restric
   }
 }
 
+// Fused GroupNorm+ReLU+Dropout backward for the SMALL pyramid levels: gn_bwd_reduce -> grid barrier -> gn_bwd_apply in
+// ONE launch.  At 24^3 and below each of the two kernels is a few microseconds of launch + prologue around almost no
+// data; the tensors stay in L2 between the phases.  Requirements (checked by the host): every CTA of the grid is
+// resident at the same time (grid <= SMs x occupancy), channel groups are a power of two <= 32 (the staged
+// reduction), fused coefficients.  `counter` is a zero-initialised word owned by this launch (one-shot barrier).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const T* __restrict__ g, long long ldg,
+                                                              const T* __restrict__ y, long long ldy,
+                                                              T* __restrict__ dy, long long ldd, double* sums,
+                                                              unsigned int* counter, int C, long long V,
+                                                              const GnRef gn, int N, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ dbias) {
+  EW_PROLOGUE(C)
+  extern __shared__ double s_dyn[];
+  double* s_d = s_dyn;                                                    // coefficient scratch (backward size)
+  float* s_f = reinterpret_cast<float*>(s_d + gn_cta_doubles(C, gn.groups, true));
+  float* s_c5 = s_f + 3 * C;                                              // [5][C]: A, B, P, Q, R
+  float* s_part = s_c5 + 5 * C;                                           // [8 warps][3][C]
+  const T* yb = y + (long long)n * V * ldy + c0;
+  const T* gb = g + (long long)n * V * ldg + c0;
+  float A[VEC], B[VEC];
+  // ---------------------------------------------------------------- phase 1: per-(n, c) sums
+  gn_cta_coefs<false>(gn, nullptr, n, C, s_d, s_f, s_c5, s_c5 + C, nullptr, nullptr, nullptr);
+  float f1[VEC], f2[VEC], f3[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    A[j] = s_c5[c0 + j];
+    B[j] = s_c5[C + c0 + j];
+    f1[j] = f2[j] = f3[j] = 0.f;
+  }
+  for (long long v = vi; v < V; v += vstep) {
+    float yv[VEC], gv[VEC];
+    Vec<T, VEC>::load(yb + v * ldy, yv);
+    Vec<T, VEC>::load(gb + v * ldg, gv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] : 0.f;
+      f1[j] += d;
+      f2[j] = fmaf(d, yv[j], f2[j]);
+      f3[j] += yv[j];
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane_groups = G < 32 ? G : 32;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    for (int off = 16; off >= lane_groups; off >>= 1) {
+      f1[j] += __shfl_xor_sync(0xffffffffu, f1[j], off);
+      f2[j] += __shfl_xor_sync(0xffffffffu, f2[j], off);
+      f3[j] += __shfl_xor_sync(0xffffffffu, f3[j], off);
+    }
+  }
+  if (lane < lane_groups) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      s_part[(wid * 3 + 0) * C + c0 + j] = f1[j];
+      s_part[(wid * 3 + 1) * C + c0 + j] = f2[j];
+      s_part[(wid * 3 + 2) * C + c0 + j] = f3[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)s_part[(w * 3 + k) * C + c];
+    atomicAdd(sums + ((long long)n * C + c) * 3 + k, t);
+  }
+  // ---------------------------------------------------------------- grid barrier (one shot)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < total) __nanosleep(20);
+    __threadfence();
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 2: dy and the parameter gradients
+  float P[VEC], Q[VEC], R[VEC];
+  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) {
+    const int cpg = C / gn.groups;
+    const double vox = gn.m / (double)cpg;
+    double dg[2] = {0.0, 0.0}, db[2] = {0.0, 0.0}, dbi[2] = {0.0, 0.0};      // channels tid, tid + 256
+    for (int nn = 0; nn < N; ++nn) {
+      const double* grp = gn_cta_coefs<true>(gn, sums, nn, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C,
+                                             s_c5 + 4 * C);
+      for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
+        const int gi_ = c / cpg;
+        const double mu = grp[gi_ * 4 + 0], rs = grp[gi_ * 4 + 1], m1 = grp[gi_ * 4 + 2], m2 = grp[gi_ * 4 + 3];
+        const double sc = (double)s_f[c], ga = (double)s_f[C + c];
+        const double* sp = sums + ((long long)nn * C + c) * 3;
+        const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
+        const double qd = -rs * rs * m2, rd = -rs * m1 + rs * rs * mu * m2;
+        db[k] += s1;
+        dg[k] += rs * (s2 - mu * s1);
+        dbi[k] += rs * ga * s1 + qd * s3 + rd * vox;
+      }
+      __syncthreads();
+    }
+    for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
+      dgamma[c] += (float)dg[k];
+      dbeta[c] += (float)db[k];
+      if (dbias != nullptr) dbias[c] = (float)dbi[k];
+    }
+  }
+  gn_cta_coefs<true>(gn, sums, n, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C, s_c5 + 4 * C);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    A[j] = s_c5[c0 + j];
+    B[j] = s_c5[C + c0 + j];
+    P[j] = s_c5[2 * C + c0 + j];
+    Q[j] = s_c5[3 * C + c0 + j];
+    R[j] = s_c5[4 * C + c0 + j];
+  }
+  T* db_ = dy + (long long)n * V * ldd + c0;
+  for (long long v = vi; v < V; v += vstep) {
+    float yv[VEC], gv[VEC], o[VEC];
+    Vec<T, VEC>::load(yb + v * ldy, yv);
+    Vec<T, VEC>::load(gb + v * ldg, gv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float d = fmaf(yv[j], A[j], B[j]) > 0.f ? gv[j] * P[j] : 0.f;
+      o[j] = d + fmaf(yv[j], Q[j], R[j]);
+    }
+    Vec<T, VEC>::store(db_ + v * ldd, o);
+  }
+}
+
 // out[c] += sum over all voxels of all samples
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
@@ -1111,6 +1239,50 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
                                                      static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
                                                      y->n, dgamma, dbeta, dbias);
+  });
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+// 1 if the fused backward can take this layer (small tensor, vectorised access, staged reduction applicable)
+int ew_gn_bwd_fused_supported(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_tensor* dy) {
+  if (!(vec_ok(g) && vec_ok(y) && vec_ok(dy))) return 0;
+  const int vec = y->dtype == B200SEG_BF16 ? 8 : 4;
+  const int G = y->c / vec;
+  if (G < 1 || G > 32 || (G & (G - 1)) != 0 || y->c > 512) return 0;
+  const long long elems = nvox(y) * y->c * (long long)y->n;
+  return elems <= (4ll << 20) ? 1 : 0;          // <= 4 Mi elements: the 24^3 x 64 level and below
+}
+
+int ew_gn_bwd_fused(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
+                    unsigned int* counter, float* dgamma, float* dbeta, float* dbias, const b200seg_tensor* dy,
+                    int device, cudaStream_t s) {
+  B200_CHECK_ARG(same_geom(g, y) && same_geom(dy, y) && g->dtype == y->dtype && dy->dtype == y->dtype,
+                 "gn_bwd_fused: tensor mismatch");
+  B200_CHECK_ARG(ew_gn_bwd_fused_supported(g, y, dy), "gn_bwd_fused: unsupported shape");
+  const long long V = nvox(y);
+  const int C = y->c;
+  const int sms = num_sms(device);
+  EW_DISPATCH(y, true, {
+    const int G = C / VEC;
+    const size_t smem = gn_cta_doubles(C, gn->groups, true) * sizeof(double) + (size_t)(8 + 24) * C * sizeof(float);
+    if (smem > 48 * 1024) {
+      static int attr_done[64] = {0};
+      if (device >= 0 && device < 64 && !attr_done[device]) {
+        B200_CUDA(cudaFuncSetAttribute(gn_bwd_fused_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       96 * 1024));
+        attr_done[device] = 1;
+      }
+    }
+    // all CTAs must be co-resident: cap the grid at one CTA per SM (the tensors are small)
+    int bx = ew_blocks(V, G, y->n, device, 1);
+    while (bx > 1 && (long long)bx * y->n > sms) --bx;
+    if ((256 % G) != 0) bx = (bx / G) * G;
+    B200_CHECK_ARG(bx >= 1 && (long long)bx * y->n <= sms, "gn_bwd_fused: batch too large for a resident grid");
+    dim3 grid(bx, y->n);
+    gn_bwd_fused_kernel<T, VEC><<<grid, 256, smem, s>>>(
+        static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, static_cast<T*>(dy->ptr), dy->ld,
+        sums, counter, C, V, make_gnref(gn, C), y->n, dgamma, dbeta, dbias);
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;

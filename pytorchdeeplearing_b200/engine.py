@@ -210,12 +210,19 @@ class Engine:
         dev = L.y.device
         vox = L.y.numel() // (n * cout)
         if L.gname is not None and L.gn is not None:
-            sums = self.zeros((n, cout, 3), torch.float64, dev)
-            be.gn_bwd_reduce_gn(g_act, L.y, L.gn, sums)
             dy = torch.empty(L.y.shape, dtype=self.T, device=dev)
-            be.gn_bwd_apply_gn(g_act, L.y, L.gn, sums, dy, self._grad_view(L.gname + ".weight"),
-                               self._grad_view(L.gname + ".bias"),
-                               self._grad_view(L.bname) if L.bname is not None else None)
+            dgam, dbet = self._grad_view(L.gname + ".weight"), self._grad_view(L.gname + ".bias")
+            dbia = self._grad_view(L.bname) if L.bname is not None else None
+            fused = getattr(be, "gn_bwd_fused_ok", None)
+            if fused is not None and fused(g_act, L.y, dy):
+                # small levels: reduce -> grid barrier -> apply in one launch (sums + one zeroed barrier word)
+                buf = self.zeros((n * cout * 3 + 2,), torch.float64, dev)
+                be.gn_bwd_fused_gn(g_act, L.y, L.gn, buf[:n * cout * 3].view(n, cout, 3), buf[n * cout * 3:], dy,
+                                   dgam, dbet, dbia)
+            else:
+                sums = self.zeros((n, cout, 3), torch.float64, dev)
+                be.gn_bwd_reduce_gn(g_act, L.y, L.gn, sums)
+                be.gn_bwd_apply_gn(g_act, L.y, L.gn, sums, dy, dgam, dbet, dbia)
         elif L.gname is not None:
             sums = self.zeros((n, cout, 3), torch.float64, dev)
             be.gn_bwd_reduce(g_act, L.y, L.coef, sums)

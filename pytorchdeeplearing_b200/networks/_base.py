@@ -70,10 +70,20 @@ class SegNetBase(nn.Module):
             return None
         if self.dropout_masks is not None:
             return [m.to(device=x.device, dtype=torch.float32) for m in self.dropout_masks]
+        # One flat buffer: every mask is drawn by its own ``bernoulli_`` call on an (N,C,1,..) view -- the same
+        # generator consumption as the reference's per-module draws -- and the 1/(1-p) scaling of all of them
+        # is a single multiply instead of one launch per layer.
         n = x.shape[0]
         ones = (1,) * self._dims
-        return [x.new_empty((n, c) + ones, dtype=torch.float32).bernoulli_(1 - P_DROP).div_(1 - P_DROP).view(n, c)
-                for c in self._mask_channels()]
+        chans = self._mask_channels()
+        flat = x.new_empty((n * sum(chans),), dtype=torch.float32)
+        masks, off = [], 0
+        for c in chans:
+            flat[off:off + n * c].view((n, c) + ones).bernoulli_(1 - P_DROP)
+            masks.append(flat[off:off + n * c].view(n, c))
+            off += n * c
+        flat.div_(1 - P_DROP)
+        return masks
 
     def forward(self, x):
         if x.dim() != self._dims + 2:

@@ -363,6 +363,42 @@ def test_groupnorm_fused_coefficient_forms(be, dtype, n, sp, c, masked):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,sp,c,masked", [(2, (24, 24, 24), 64, True), (2, (12, 12, 12), 128, True),
+                                           (2, (6, 6, 6), 256, False), (3, (4, 6, 8), 16, True),
+                                           (1, (1, 64, 64), 32, True)])
+def test_groupnorm_backward_single_launch(be, dtype, n, sp, c, masked):
+    """b200seg_gn_bwd_fused_gn (reduce -> grid barrier -> apply in one launch) against the two-launch form"""
+    g = torch.Generator().manual_seed(37)
+    y = sliced(n, sp, c, dtype, g, pad=16).cuda()
+    gact = rnd((n,) + sp + (c,), dtype, g).cuda()
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)).cuda()
+    beta = (0.2 * torch.randn(c, generator=g)).cuda()
+    scale = ((torch.rand(n, c, generator=g) > 0.2).float() / 0.8).cuda() if masked else None
+    vox = sp[0] * sp[1] * sp[2]
+    yf = y.double()
+    stats = torch.stack([yf.sum((1, 2, 3)), (yf * yf).sum((1, 2, 3))], -1).contiguous()
+    gn = (stats, gamma, beta, scale, vox, 8, 1e-5)
+    dy_a = torch.empty((n,) + sp + (c,), dtype=dtype, device="cuda")
+    dy_b = torch.empty_like(dy_a)
+    if not be.gn_bwd_fused_ok(gact, y, dy_b):
+        assert dtype == torch.float32 and c // 4 > 32      # fp32: more than 32 channel groups per voxel
+        pytest.skip("shape stays on the two-launch form")
+    sums = torch.zeros(n, c, 3, dtype=torch.float64, device="cuda")
+    dg_a, db_a, dbi_a = torch.ones(c, device="cuda"), torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    be.gn_bwd_reduce_gn(gact, y, gn, sums)
+    be.gn_bwd_apply_gn(gact, y, gn, sums, dy_a, dg_a, db_a, dbi_a)
+    for _ in range(3):                       # repeated launches: the one-shot barrier word is fresh each time
+        buf = torch.zeros(n * c * 3 + 2, dtype=torch.float64, device="cuda")
+        dg_b, db_b, dbi_b = torch.ones(c, device="cuda"), torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        be.gn_bwd_fused_gn(gact, y, gn, buf[:n * c * 3].view(n, c, 3), buf[n * c * 3:], dy_b, dg_b, db_b, dbi_b)
+        torch.cuda.synchronize()
+        assert rel(buf[:n * c * 3].view(n, c, 3), sums) < 1e-5      # fp32 thread partials, different grids
+        assert rel(dy_b, dy_a) < tol(dtype, 0.1)
+        assert rel(dg_b, dg_a) < 1e-5 and rel(db_b, db_a) < 1e-5
+        assert (dbi_b - dbi_a).abs().max() < 1e-4 * (1 + dbi_a.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_multi_tensor_pack_and_unpack(be, dtype):
     """b200seg_pack_weights_multi / b200seg_unpack_wgrads_multi (tap-contiguous smem-transposed paths and the
     generic path) against the single-tensor entry points, for every operand layout the engine requests."""
