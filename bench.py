@@ -163,6 +163,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# stdout hygiene: libraries (NCCL's version banner, ...) write to file descriptor 1 directly.  While the bench runs,
+# fd 1 points at stderr; the one JSON line is emitted through the saved descriptor.
+# ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # per-kernel timing wrapper (instrumentation around the real CudaBackend)
 # ------------------------------------------------------------------------------------------------
 class TimedBackend:
@@ -278,7 +300,7 @@ def run_reference(args):
                              "sample": f"{steps} full steps ({WL_DESC}) of the oracle restatement on "
                                        f"{torch.get_num_threads()} host threads"},
             "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def pick_cpu_threads():
@@ -336,6 +358,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="vnet3d96", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    _capture_stdout()
     select_workload(args.workload)
     args.warmup = max(3, args.warmup)
 
@@ -521,7 +544,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
