@@ -19,6 +19,8 @@ the reference (VNet3d.py:13-15, Unet3d.py:66-85) is executed as
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -54,6 +56,21 @@ def _taps(kind: int, dims: int) -> int:
     if kind == K1:
         return 1
     return 8 if dims == 3 else 4
+
+
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device) -> Optional["torch.cuda.Stream"]:
+    """Second stream for the weight gradients (independent of the data-gradient chain once dy exists); joins the
+    main stream again in ``_finish_backward``.  Works under CUDA-graph capture (fork/join become graph edges)."""
+    if device.type != "cuda" or os.environ.get("B200SEG_WGRAD_SIDE_STREAM", "1") == "0":
+        return None
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st
 
 
 class _ZeroArena:
@@ -95,6 +112,8 @@ class Engine:
         self._z32 = None
         self._packs: Dict[Tuple[str, str], object] = {}
         self._unpack_list: List[Tuple[Tensor, Tensor]] = []
+        self._side = None                      # side stream carrying this pass's weight gradients (if any)
+        self._side_keep: List[object] = []     # operands of side-stream kernels stay referenced until the join
 
     # ---------------------------------------------------------------- allocation helpers
     def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
@@ -136,6 +155,10 @@ class Engine:
         self._packs = dict(zip(keys, self.be.pack_many(reqs)))
 
     def _finish_backward(self) -> None:
+        if self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            self._side = None
+        self._side_keep = []
         self.be.unpack_many(self._unpack_list)
         self._unpack_list = []
         self._packs = {}
@@ -241,10 +264,20 @@ class Engine:
         cin = L.x.shape[-1]
         if L.kind == UP:
             dwp = self.zeros((taps, cout, cin), torch.float32, dev)
-            be.wgrad(DOWN, self.dims, dy, L.x, dwp)          # a = fine side (dy), b = coarse side (x)
+            wg = (DOWN, self.dims, dy, L.x, dwp)             # a = fine side (dy), b = coarse side (x)
         else:
             dwp = self.zeros((taps, cin, cout), torch.float32, dev)
-            be.wgrad(L.kind, self.dims, L.x, dy, dwp)
+            wg = (L.kind, self.dims, L.x, dy, dwp)
+        side = _side_stream(dev) if need_dx else None        # nothing to overlap with when there is no dgrad
+        if side is not None:
+            # dW only feeds the final unpack: run it beside the dgrad -> next-layer chain
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                be.wgrad(*wg)
+            self._side = side
+            self._side_keep.append(wg)
+        else:
+            be.wgrad(*wg)
         self._unpack_list.append((dwp, self._grad_view(L.wname)))
         if not need_dx:
             return None
