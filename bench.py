@@ -457,13 +457,39 @@ def main():
 
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
+    host_losses = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_values = []
+
+    def e2e_loop(k):
+        """k steps through the public API with HOST inputs, software-pipelined the way a training loop runs around a
+        CUDA graph: the inputs of step i+1 are copied from pinned host memory on a copy stream while step i
+        executes, and the loss of step i is copied back asynchronously and READ ON THE HOST while step i+1 executes
+        (one step of lag, every loss is read).  One timed region around the whole loop: all k H2D copies and all k
+        D2H reads are inside it.  Returns ms per step."""
+        torch.cuda.synchronize()
+        loss_values.clear()
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         if use_graph:
-            loss = graphed(xh, yh)
-        else:
-            loss = eager_step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
-        host_loss.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller has the loss value on the host
+            graphed.prefetch(xh, yh)
+        for i in range(k):
+            if use_graph:
+                loss = graphed(prefetched=True)
+                if i + 1 < k:
+                    graphed.prefetch(xh, yh)
+            else:
+                loss = eager_step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
+            host_losses[i & 1].copy_(loss.detach(), non_blocking=True)
+            done[i & 1].record()
+            if i > 0:                                       # the previous step's loss is on the host by now
+                done[(i - 1) & 1].synchronize()
+                loss_values.append(float(host_losses[(i - 1) & 1]))
+        done[(k - 1) & 1].synchronize()
+        loss_values.append(float(host_losses[(k - 1) & 1]))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
 
     for _ in range(args.warmup):
         resident_step()
@@ -476,10 +502,9 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        e2e_step()
+    e2e_loop(2)
     barrier()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = [e2e_loop(args.steps)] * args.steps
     barrier()
 
     tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
@@ -532,7 +557,10 @@ def main():
                                    " + bwd of all parameter tensors"
                                    + (" + NCCL SUM all-reduce of the flat fp32 gradient bucket" if world > 1 else ""),
                        "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
-                       "l2": "256 MiB flush before every timed step; per-step working set > 1 GB >> 126 MB L2",
+                       "l2": "value: 256 MiB flush before every timed step; e2e: one timed region over all steps, "
+                             "no flush (inputs arrive from the host every step; per-step working set > 1 GB >> 126 MB L2)",
+                       "e2e_pipeline": "H2D of step i+1 on a copy stream overlaps step i; the loss of every step is "
+                                       "copied back and read on the host while the next step runs (one step of lag)",
                        "cuda_graph": bool(use_graph and (graphed.graph is not None or graphed.graph_a is not None)),
                        "precision_mode": args.precision},
             "e2e": {"value": vox_step / t_e2e, "unit": "voxels/s", "ms_per_step": t_e2e * 1e3,

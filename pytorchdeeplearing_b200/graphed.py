@@ -8,6 +8,7 @@ launches once (static shapes, static input/output buffers) and replays them with
 
     step = GraphedStep(model, lossfn, x_example, y_example)
     loss = step(x, y)            # copies x, y into the static buffers, replays, returns the loss tensor
+    step.prefetch(x2, y2); loss = step(prefetched=True)   # pipelined form: the H2D copy overlaps the previous step
     # model.parameters() .grad now hold this step's gradients (static tensors, overwritten per replay)
 
 Single GPU: ONE graph holds ``model(x) -> lossfn -> loss.backward()`` exactly as a user writes it.
@@ -144,8 +145,44 @@ class GraphedStep:
         for p, g in zip(self.model.parameters(), self._grads):
             p.grad = g
 
+    # ------------------------------------------------------------------ input prefetch
+    def prefetch(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Start the host->device copy of the NEXT step's inputs on a copy stream (pinned host tensors) while the
+        current step is still running; ``step(prefetched=True)`` then only moves them device-to-device into the
+        static buffers.  This is the input pipeline a training loop would run around the graph."""
+        if not self.x.is_cuda:
+            self._staged_host = (x, y)
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.x.device)
+            self._sx, self._sy = torch.empty_like(self.x), torch.empty_like(self.y)
+            self._staged_ev = torch.cuda.Event()
+            self._free_ev = torch.cuda.Event()
+            self._free_ev.record(torch.cuda.current_stream(self.x.device))
+        cs = self._copy_stream
+        cs.wait_event(self._free_ev)                 # the previous step has drained the staging buffers
+        with torch.cuda.stream(cs):
+            self._sx.copy_(x, non_blocking=True)
+            self._sy.copy_(y, non_blocking=True)
+            self._staged_ev.record(cs)
+
+    def _take_prefetched(self) -> None:
+        if not self.x.is_cuda:
+            x, y = self._staged_host
+            self.x.copy_(x)
+            self.y.copy_(y)
+            return
+        main = torch.cuda.current_stream(self.x.device)
+        main.wait_event(self._staged_ev)
+        self.x.copy_(self._sx, non_blocking=True)
+        self.y.copy_(self._sy, non_blocking=True)
+        self._free_ev.record(main)
+
     # ------------------------------------------------------------------ replay
-    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
+                 prefetched: bool = False) -> torch.Tensor:
+        if prefetched:
+            self._take_prefetched()
         if x is not None:
             self.x.copy_(x, non_blocking=True)
         if y is not None:
