@@ -89,6 +89,10 @@ typedef struct b200seg_pack_desc {
 } b200seg_pack_desc;
 int b200seg_pack_weights_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,
                                b200seg_stream stream);
+/* Copy a small host array (descriptor table; bytes % 16 == 0, 16-byte aligned destination) to device memory through
+ * KERNEL ARGUMENTS instead of a memcpy: inside a captured step this keeps the copy engines free for the caller's own
+ * input prefetch (a memcpy node would queue behind it and stall the graph).  The host array is read during the call. */
+int b200seg_upload_table(const void* host_table, int64_t bytes, void* device_dst, int device, b200seg_stream stream);
 int b200seg_unpack_wgrads_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,
                                 b200seg_stream stream);
 

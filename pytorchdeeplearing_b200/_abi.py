@@ -48,6 +48,7 @@ _SIGNATURES = {
     "b200seg_unpack_wgrad": ([_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp], C.c_int),
     "b200seg_pack_weights_multi": ([_vp, _i, _i, _i, _vp], C.c_int),
     "b200seg_unpack_wgrads_multi": ([_vp, _i, _i, _i, _vp], C.c_int),
+    "b200seg_upload_table": ([_vp, _i64, _vp, _i, _vp], C.c_int),
     "b200seg_conv": ([_i, _i, _PT, _vp, _i, _vp, _PT, _vp, _PT, _i, _vp], C.c_int),
     "b200seg_conv_tc_eligible": ([_i, _i, _i], C.c_int),
     "b200seg_conv_halo_eligible": ([_i, _i, _i], C.c_int),
@@ -246,19 +247,17 @@ class CudaBackend:
         return PackedWeight(out, code, w, kind, which, dims)
 
     def _table_to_device(self, descs, device):
-        """ctypes descriptor array -> pinned host tensor -> device tensor (async copy on the current stream)."""
+        """ctypes descriptor array -> device tensor, written by a kernel that receives the bytes as ARGUMENTS (no
+        host-to-device memcpy: see b200seg_upload_table)."""
         arr = (PackDesc * len(descs))(*descs)
-        raw = bytes(arr)
-        host = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
-        host.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
-        devt = host.to(device, non_blocking=True)
-        # the pinned buffer must outlive the (possibly graph-captured) copy
-        if torch.cuda.is_current_stream_capturing():
-            self._pinned_forever.append(host)
-        else:
-            self._pinned_ring.append(host)
-            if len(self._pinned_ring) > 32:
-                self._pinned_ring.pop(0)
+        nbytes = C.sizeof(arr)
+        pad = (nbytes + 15) // 16 * 16
+        buf = (C.c_char * pad)()
+        C.memmove(buf, arr, nbytes)
+        devt = torch.empty(pad, dtype=torch.uint8, device=device)
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        self._check(self.lib.b200seg_upload_table(C.cast(buf, C.c_void_p), pad, devt.data_ptr(), dev,
+                                                  torch.cuda.current_stream(dev).cuda_stream))
         return devt
 
     def pack_many(self, reqs):

@@ -76,6 +76,7 @@ int ew_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N
 int ew_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, long long st, long long sk, long long sn,
                     cudaStream_t s);
 int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack, cudaStream_t s);
+int ew_upload_table(const void* host, long long bytes, void* dev_dst, cudaStream_t s);
 int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale, int N, int C,
                    int groups, long long vox, float eps, float* coef, float* mr, cudaStream_t s);
 int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, const b200seg_tensor* y2,
@@ -149,6 +150,12 @@ int b200seg_pack_weights_multi(const b200seg_pack_desc* table, int count, int to
   B200_CHECK_ARG(table != nullptr && count >= 0 && total_blocks >= 0, "b200seg_pack_weights_multi: bad argument");
   B200_DEVICE(device);
   return ew_pack_multi(table, count, total_blocks, 0, ST(stream));
+}
+
+int b200seg_upload_table(const void* host_table, int64_t bytes, void* device_dst, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(host_table != nullptr && device_dst != nullptr && bytes > 0, "b200seg_upload_table: bad argument");
+  B200_DEVICE(device);
+  return ew_upload_table(host_table, bytes, device_dst, ST(stream));
 }
 
 int b200seg_unpack_wgrads_multi(const b200seg_pack_desc* table, int count, int total_blocks, int device,

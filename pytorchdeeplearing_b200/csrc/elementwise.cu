@@ -5,6 +5,8 @@
 // All activation kernels use 128-bit accesses along the channel dimension of the NDHWC layout
 // (VEC = 8 bf16 / 4 fp32 channels per thread); the grid is sized so that a thread's channel group
 // never changes across its grid-stride loop, hence the per-(n,c) coefficients live in registers.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace b200seg {
@@ -208,6 +210,32 @@ __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __res
     const int t = (int)(r / d.K);
     out[t * d.st + k * d.sk + n * d.sn2] = d.src[i];
   }
+}
+
+// Descriptor tables reach the device as KERNEL ARGUMENTS (<= 3968 bytes per launch), not through a host-to-device
+// memcpy: a memcpy node inside the step's CUDA graph queues on the copy engine behind the application's own input
+// prefetch (tens of MB per step) and stalls the whole graph for the duration of that transfer.
+struct TableChunk {
+  unsigned char b[3968];
+};
+__global__ void table_write_kernel(const __grid_constant__ TableChunk c, unsigned char* __restrict__ dst, int n) {
+  for (int i = threadIdx.x * 16; i < n; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(c.b + i);
+}
+
+int ew_upload_table(const void* host, long long bytes, void* dev_dst, cudaStream_t s) {
+  B200_CHECK_ARG((bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(dev_dst) % 16) == 0,
+                 "upload_table: size and destination must be multiples of 16 bytes");
+  const unsigned char* src = static_cast<const unsigned char*>(host);
+  unsigned char* dst = static_cast<unsigned char*>(dev_dst);
+  for (long long off = 0; off < bytes; off += (long long)sizeof(TableChunk)) {
+    const int n = (int)((bytes - off) < (long long)sizeof(TableChunk) ? (bytes - off) : (long long)sizeof(TableChunk));
+    TableChunk c;
+    memcpy(c.b, src + off, (size_t)n);
+    table_write_kernel<<<1, 256, 0, s>>>(c, dst + off, n);
+  }
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
 }
 
 int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack, cudaStream_t s) {

@@ -41,3 +41,32 @@ def e():   # serial H2D on the main stream (old e2e)
 for name, fn in (("replay only", a), ("+ async D2H of loss", b), ("+ D2D take", c), ("+ H2D prefetch on copy stream", d), ("H2D on main stream", e)):
     region(fn)
     print(f"{name:34s} {region(fn):.3f} ms/step", flush=True)
+
+# ---- isolate: does an independent H2D copy on another stream overlap a graph replay at all?
+cs = torch.cuda.Stream()
+sx, sy = torch.empty_like(x), torch.empty_like(y)
+def h2d_only():
+    for _ in range(K):
+        with torch.cuda.stream(cs):
+            sx.copy_(xh, non_blocking=True); sy.copy_(yh, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(cs)
+def replay_plus_free_h2d():
+    for _ in range(K):
+        g.graph.replay()
+        with torch.cuda.stream(cs):
+            sx.copy_(xh, non_blocking=True); sy.copy_(yh, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(cs)
+big = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+def memset_plus_free_h2d():      # a plain (non-graph) long kernel instead of the graph
+    for _ in range(K):
+        for _ in range(8): big.zero_()
+        with torch.cuda.stream(cs):
+            sx.copy_(xh, non_blocking=True); sy.copy_(yh, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(cs)
+def memset_only():
+    for _ in range(K):
+        for _ in range(8): big.zero_()
+for name, fn in (("H2D alone (21 MB)", h2d_only), ("replay + independent H2D", replay_plus_free_h2d),
+                 ("8 memsets alone", memset_only), ("8 memsets + independent H2D", memset_plus_free_h2d)):
+    region(fn)
+    print(f"{name:34s} {region(fn):.3f} ms/step", flush=True)
