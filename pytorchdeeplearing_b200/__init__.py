@@ -15,9 +15,10 @@ from .losses import (BinaryDiceLoss, BinaryCrossEntropyLoss, BinaryFocalLoss, Bi
                      BinaryDiceFocalLoss, MutilCrossEntropyLoss, MutilFocalLoss, MutilDiceLoss,
                      MutilCrossEntropyDiceLoss)
 from .install import install, uninstall
+from .graphed import GraphedStep
 
 __all__ = ["VNet3d", "UNet3d", "UNet2d", "initialize_weights", "set_precision", "get_precision",
-           "enable_data_parallel", "disable_data_parallel", "install", "uninstall",
+           "enable_data_parallel", "disable_data_parallel", "install", "uninstall", "GraphedStep",
            "BinaryDiceLoss", "BinaryCrossEntropyLoss", "BinaryFocalLoss", "BinaryCrossEntropyDiceLoss",
            "BinaryDiceFocalLoss", "MutilCrossEntropyLoss", "MutilFocalLoss", "MutilDiceLoss",
            "MutilCrossEntropyDiceLoss"]
