@@ -11,10 +11,11 @@
 //   B tile  : TMA 2-D load of the [tap*Cout + co][ci] packed weights (K-major, same swizzle).
 //   MMA     : one elected thread issues BKC/16 tcgen05.mma (M128 x N x K16) per stage into a TMEM
 //             accumulator; tcgen05.commit releases the smem stage / publishes the accumulator.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
-// epilogue (tcgen05.ld -> +bias -> GroupNorm sum/sumsq partials -> +addend -> bf16 NDHWC stores).
-// Two accumulator stages in TMEM overlap the epilogue of tile i with the main loop of tile i+1;
-// CTAs are persistent over contiguous tile ranges (grid = min(tiles, #SM)).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-9 epilogue in two groups
+// of four (one warp per TMEM lane quarter; group e drains the tiles with local index = e mod 2):
+// tcgen05.ld -> +bias -> GroupNorm sum/sumsq partials -> +addend -> bf16 NDHWC stores.
+// Up to four accumulator stages in TMEM let the MMA issuer run ahead of the epilogue; CTAs are persistent over
+// contiguous tile ranges (grid = min(tiles, #SM)).
 #include <stdlib.h>
 
 #include "tc_common.cuh"

@@ -175,3 +175,23 @@ def test_graphed_step_split_phases_match_autograd_path():
     finally:
         b200.disable_data_parallel()
         dist.destroy_process_group()
+
+
+def test_graphed_step_prefetch_matches_direct_inputs():
+    """GraphedStep.prefetch + step(prefetched=True) (the pipelined input path of bench.py's e2e loop) feeds the same
+    inputs as step(x, y); on CPU the staging is a plain copy."""
+    from pytorchdeeplearing_b200.graphed import GraphedStep
+    spec, sd, model, ofwd, draw = _build("vnet3d", 1, 2, seed=3)
+    model.eval()                                       # no dropout draws: the two paths must agree exactly
+    lossfn = b200.MutilDiceLoss(torch.ones(2))
+    x0, y0 = oracle.make_inputs(1, 1, (16, 16, 16), 2, seed=11)
+    x1, y1 = oracle.make_inputs(1, 1, (16, 16, 16), 2, seed=12)
+    step = GraphedStep(model, lossfn, x0, y0, warmup=1, use_graph=False)
+    l_direct = float(step(x1, y1))
+    g_direct = [p.grad.clone() for p in model.parameters()]
+    step(x0, y0)
+    step.prefetch(x1, y1)
+    l_pref = float(step(prefetched=True))
+    assert l_pref == l_direct
+    for a, p in zip(g_direct, model.parameters()):
+        assert torch.equal(a, p.grad)
