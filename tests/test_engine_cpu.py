@@ -187,11 +187,11 @@ def test_graphed_step_prefetch_matches_direct_inputs():
     x0, y0 = oracle.make_inputs(1, 1, (16, 16, 16), 2, seed=11)
     x1, y1 = oracle.make_inputs(1, 1, (16, 16, 16), 2, seed=12)
     step = GraphedStep(model, lossfn, x0, y0, warmup=1, use_graph=False)
-    l_direct = float(step(x1, y1))
+    l_direct = float(step(x1, y1).detach())
     g_direct = [p.grad.clone() for p in model.parameters()]
     step(x0, y0)
     step.prefetch(x1, y1)
-    l_pref = float(step(prefetched=True))
+    l_pref = float(step(prefetched=True).detach())
     assert l_pref == l_direct
     for a, p in zip(g_direct, model.parameters()):
         assert torch.equal(a, p.grad)
