@@ -164,7 +164,7 @@ class CudaBackend:
         self.halo_min_vox = int(os.environ.get("B200SEG_HALO_MIN_VOX", str(128 * 128)))
         self.use_halo_ws = os.environ.get("B200SEG_DISABLE_HALO_WS", "0") != "1"
         self.halo_ws_min_vox = int(os.environ.get("B200SEG_HALO_WS_MIN_VOX", "1000"))
-        self._pinned_forever, self._pinned_ring, self._keep_tables = [], [], []
+        self._keep_tables = []     # device descriptor tables stay referenced while launches that read them may be pending
         self.launch_count = 0      # kernels launched through the C ABI (one per successful entry-point call)
 
     # ------------------------------------------------------------------ plumbing
@@ -298,6 +298,8 @@ class CudaBackend:
         table = self._table_to_device(descs, items[0][0].device)
         self._check(self.lib.b200seg_unpack_wgrads_multi(table.data_ptr(), len(descs), blocks, dev, st))
         self._keep_tables.append(table)
+        if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
+            self._keep_tables.pop(0)
 
     def unpack_wgrad(self, dwp, grad, kind, dims):
         t, k, n = dwp.shape
