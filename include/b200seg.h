@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_VERSION 100
+#define B200SEG_VERSION 200
 
 #define B200SEG_OK 0
 #define B200SEG_EINVAL (-1)   /* bad argument / unsupported combination */
@@ -39,6 +39,8 @@ extern "C" {
 #define B200SEG_BF16_HALO 3 /* weights only: bf16 packed [tap][K/8][N][8] (smem image of the halo-staged 3x3x3 path) */
 #define B200SEG_BF16_HALO_WS 4 /* weights only: bf16 packed [N/NT][tap][K/8][NT][8], NT = b200seg_conv_halo_ws_ntile():
                                   per-group tap blocks streamed by the 64/128-channel halo-staged 3x3x3 path */
+
+#define B200SEG_I64 16 /* labels only: int64 class indices (model/dataset.py:114); B200SEG_F32 = soft binary targets */
 
 /* conv kinds */
 #define B200SEG_K3 0    /* 3x3x3 (dims==3) or 1x3x3 (dims==2), stride 1, zero pad 1 */
@@ -183,7 +185,7 @@ int b200seg_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* g_out, const
 
 /* ---- fused head (OutputTransition3d, VNet3d.py:90-99; Unet3d.py:56-61): 1x1 conv to `nc` <= 8 classes + bias,
  * then sigmoid (nc == 1) or softmax over classes.  w: the nn.Conv parameter itself, fp32 [nc][Cin]; logits and
- * probs: fp32 channels-last [voxels][nc]. */
+ * probs: fp32 channels-last [voxels][nc]; probs may be NULL (logits only). */
 int b200seg_head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* logits, float* probs, int nc,
                      int device, b200seg_stream stream);
 /* backward of the head conv in one pass: dx = dlogits * W (same dtype as x), dw[nc][Cin] += dlogits^T x,
@@ -196,15 +198,55 @@ int b200seg_head_bwd(const b200seg_tensor* x, const float* dlogits, const float*
 /* ---- head activation: torch.sigmoid / torch.softmax(dim=1) (VNet3d.py:95-98; Unet3d.py:58-61) */
 int b200seg_head_probs(const float* logits, float* probs, int64_t nvox, int C, int device, b200seg_stream stream);
 
-/* ---- losses (model/losses.py:33-53,129-197,247-342), logits fp32 channels-last [nvox][C], labels int64
- * part (double, += ): C>1: I_c[C], P_c[C], Cnt_c[C], sum_nll, sum_focal, V ; C==1: I, P, T, sum_bce, sum_focal, V */
-int b200seg_loss_partials(const float* logits, const int64_t* labels, int64_t nvox, int C, float gamma, float alpha_f,
-                          double* part, int device, b200seg_stream stream);
+/* ---- losses (model/losses.py:33-53,129-197,247-342), logits fp32 channels-last [N][vox][C]; labels [N][vox] int64
+ * (B200SEG_I64) or, for the binary losses only, fp32 soft targets (B200SEG_F32: ``y_true.float()`` losses.py:47,144).
+ * part (double, += ): C>1: I_c[C], P_c[C], Cnt_c[C], sum_nll, sum_focal, V, BAD ; C==1: I, P, T, sum_bce, sum_focal,
+ * V, BAD -- BAD counts labels outside [0, C) (the reference raises in F.one_hot / F.cross_entropy, losses.py:254,311:
+ * such voxels are skipped, b200seg_loss_finalize turns the loss into NaN and the host binding raises).
+ * metric (double [N][C][3], += , or NULL): per sample and class {sum [p_c>.5][t==c], sum [p_c>.5], sum [t==c]} -- the
+ * sums of the per-step accuracy (dice_coeff / multiclass_dice_coeff, model/metric.py:146-181, called every step at
+ * model/modelVNet.py:582) from the SAME read of logits + labels. */
+int b200seg_loss_partials(const float* logits, const void* labels, int label_dtype, int N, int64_t vox_per_sample,
+                          int C, float gamma, float alpha_f, double* part, double* metric, int device,
+                          b200seg_stream stream);
 /* lcoef (fp32): C>1: a_c[C], b_c[C], ce_scale, focal_scale, gamma ; C==1: a, b, bce_scale, focal_scale, gamma */
 int b200seg_loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f,
                           float* loss, float* lcoef, int device, b200seg_stream stream);
-int b200seg_loss_bwd(const float* logits, const int64_t* labels, int64_t nvox, int C, const float* lcoef,
-                     const float* gscale, float* dlogits, int device, b200seg_stream stream);
+int b200seg_loss_bwd(const float* logits, const void* labels, int label_dtype, int64_t nvox, int C,
+                     const float* lcoef, const float* gscale, float* dlogits, int device, b200seg_stream stream);
+
+/* ---- per-step accuracy (model/metric.py:146-181).  b200seg_metric_partials: the sums above from MATERIALISED
+ * probabilities (fp32 channels-last [N][vox][C], threshold 0.5 in the reference); b200seg_metric_finalize:
+ * out[0] = dice_coeff (C == 1) / multiclass_dice_coeff (mean over classes 1..C-1), out[1] = the iou_coeff analogue. */
+int b200seg_metric_partials(const float* probs, const void* labels, int label_dtype, int N, int64_t vox_per_sample,
+                            int C, float threshold, double* metric, int device, b200seg_stream stream);
+int b200seg_metric_finalize(const double* metric, int N, int C, float* out /*[2]*/, int device, b200seg_stream stream);
+
+/* ---- fused optimizer step over FLAT fp32 buffers (torch.optim.AdamW(lr) model/modelVNet.py:548, weight_decay 0.01,
+ * decoupled = 1; torch.optim.Adam model/modelUnet.py:849, decoupled = 0): ONE launch for all parameters instead of
+ * ~6 foreach launches over 128 tensors.  state (fp32 [4], device): [0] step count t, [1] lr/(1-b1^t), [2]
+ * sqrt(1-b2^t); tick != 0 advances t first (one extra 1-thread launch) so a captured step replays correctly.
+ * gscale: optional device scalar multiplied into the gradient (e.g. 1/world for an averaged all-reduce) or NULL. */
+int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                      const float* gscale, int tick, int device, b200seg_stream stream);
+
+/* ---- ALL dropout channel masks of one forward in one launch (nn.Dropout3d/2d(p), VNet3d.py:11,31,51,67;
+ * Unet3d.py:74,83): out[first_k + i] = keep(k, j0_k + i) ? 1/(1-p) : 0 for i < count_k, where keep(k, j) is exactly
+ * element j of what the k-th ``x.new_empty((N,C_k,1,..)).bernoulli_(1-p)`` of a forward draws from a CUDA generator
+ * at {seed, offset} = rng[0], rng[1] (device memory; Philox4_32_10, the k-th call sees offset + 4k).  The caller
+ * advances its generator by 4*nmasks.  table: device int32 [nmasks][3] = {first_k, count_k, j0_k}; j0_k != 0 lets a
+ * data-parallel rank take its slice of the global-batch draw. */
+int b200seg_dropout_masks(const int64_t* rng, const int32_t* table, int nmasks, int total, double p_drop, float* out,
+                          int device, b200seg_stream stream);
+
+/* ---- forward-only head for inference (predict, model/modelVNet.py:655-676): 1x1 conv to nc <= 8 classes, then
+ * mask = (sigmoid > threshold) * 255 (nc == 1) or argmax over classes (first maximum, as np.argmax) -> uint8
+ * [voxels]; neither logits nor probs are written.  b200seg_mask_logits: the same from fp32 channels-last logits. */
+int b200seg_head_mask(const b200seg_tensor* x, const float* w, const float* bias, uint8_t* mask, int nc,
+                      float threshold, int device, b200seg_stream stream);
+int b200seg_mask_logits(const float* logits, int64_t nvox, int C, float threshold, uint8_t* mask, int device,
+                        b200seg_stream stream);
 
 #ifdef __cplusplus
 }

@@ -25,12 +25,13 @@ EPS = 1e-5            # torch default GroupNorm eps
 # --------------------------------------------------------------------------------------
 # state_dict layouts, in registration order
 # --------------------------------------------------------------------------------------
-def vnet3d_state_spec(image_channel: int, numclass: int, f: int = 16) -> List[Tuple[str, Tuple[int, ...]]]:
-    """Names/shapes of VNet3d's 128 tensors (networks/VNet3d.py:25-127)."""
+def vnet3d_state_spec(image_channel: int, numclass: int, f: int = 16, dims: int = 3) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Names/shapes of VNet3d's 128 tensors (networks/VNet3d.py:25-127); ``dims=2``: VNet2d (networks/VNet2d.py:25-127,
+    the same tree with 2-D kernels)."""
     spec: List[Tuple[str, Tuple[int, ...]]] = []
 
     def conv(name, co, ci, k):
-        spec.append((name + ".weight", (co, ci, k, k, k)))
+        spec.append((name + ".weight", (co, ci) + (k,) * dims))
         spec.append((name + ".bias", (co,)))
 
     def gn(name, c):
@@ -49,7 +50,7 @@ def vnet3d_state_spec(image_channel: int, numclass: int, f: int = 16) -> List[Tu
             gn(f"{name}.ops.{i}.bn1", co)             # VNet3d.py:9
     for name, ci, co, n in (("up_tr256", 16 * f, 8 * f, 3), ("up_tr128", 8 * f, 4 * f, 3),
                             ("up_tr64", 4 * f, 2 * f, 2), ("up_tr32", 2 * f, f, 1)):
-        spec.append((name + ".up_conv.weight", (ci, co, 2, 2, 2)))   # ConvTranspose3d, VNet3d.py:65
+        spec.append((name + ".up_conv.weight", (ci, co) + (2,) * dims))   # ConvTranspose3d, VNet3d.py:65
         spec.append((name + ".up_conv.bias", (co,)))
         gn(name + ".bn", co)                          # VNet3d.py:66
         for i in range(n):                            # VNet3d.py:69
@@ -136,8 +137,8 @@ def unet_mask_channels(f: int = 16) -> List[int]:
     return ch
 
 
-def draw_dropout_masks_vnet3d(n: int, f: int = 16, device="cpu", dtype=torch.float32) -> List[Tensor]:
-    return [_draw(n, c, 3, device, dtype) for c in vnet3d_mask_channels(f)]
+def draw_dropout_masks_vnet3d(n: int, f: int = 16, device="cpu", dtype=torch.float32, dims: int = 3) -> List[Tensor]:
+    return [_draw(n, c, dims, device, dtype) for c in vnet3d_mask_channels(f)]
 
 
 def draw_dropout_masks_unet(n: int, dims: int, f: int = 16, device="cpu", dtype=torch.float32) -> List[Tensor]:
@@ -167,33 +168,36 @@ def _gdr(x: Tensor, gamma: Tensor, beta: Tensor, mk: _Masks) -> Tensor:
 
 def vnet3d_forward(sd: Dict[str, Tensor], x: Tensor, masks: Optional[Sequence[Tensor]] = None,
                    f: int = 16) -> Tuple[Tensor, Tensor]:
-    """VNet3d.forward (networks/VNet3d.py:129-158). Returns (logits, probs)."""
+    """VNet3d.forward (networks/VNet3d.py:129-158); a 4-D input runs VNet2d.forward (networks/VNet2d.py:129-158,
+    the same graph with 2-D ops).  Returns (logits, probs)."""
     mk = _Masks(masks)
+    conv3d = F.conv3d if x.dim() == 5 else F.conv2d
+    convT3d = F.conv_transpose3d if x.dim() == 5 else F.conv_transpose2d
     p = "in_tr."
     # InputTransition3d.forward, VNet3d.py:34-43 (one bn1 shared by both branches)
-    a = _gdr(F.conv3d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1),
+    a = _gdr(conv3d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1),
              sd[p + "bn1.weight"], sd[p + "bn1.bias"], mk)
-    b = _gdr(F.conv3d(x, sd[p + "conv2.weight"], sd[p + "conv2.bias"]),
+    b = _gdr(conv3d(x, sd[p + "conv2.weight"], sd[p + "conv2.bias"]),
              sd[p + "bn1.weight"], sd[p + "bn1.bias"], mk)
     out16 = a + b
 
     def lu_stack(prefix: str, h: Tensor, n: int) -> Tensor:
         for i in range(n):                                             # VNet3d.py:13-15
             q = f"{prefix}.ops.{i}."
-            h = _gdr(F.conv3d(h, sd[q + "conv1.weight"], sd[q + "conv1.bias"], padding=1),
+            h = _gdr(conv3d(h, sd[q + "conv1.weight"], sd[q + "conv1.bias"], padding=1),
                      sd[q + "bn1.weight"], sd[q + "bn1.bias"], mk)
         return h
 
     def down(prefix: str, h: Tensor, n: int) -> Tensor:                # VNet3d.py:55-59
-        d = _gdr(F.conv3d(h, sd[prefix + ".down_conv.weight"], sd[prefix + ".down_conv.bias"], stride=2),
+        d = _gdr(conv3d(h, sd[prefix + ".down_conv.weight"], sd[prefix + ".down_conv.bias"], stride=2),
                  sd[prefix + ".bn1.weight"], sd[prefix + ".bn1.bias"], mk)
         return lu_stack(prefix, d, n) + d
 
     def up(prefix: str, h: Tensor, skip: Tensor, n: int) -> Tensor:    # VNet3d.py:72-80
-        u = _gdr(F.conv_transpose3d(h, sd[prefix + ".up_conv.weight"], sd[prefix + ".up_conv.bias"], stride=2),
+        u = _gdr(convT3d(h, sd[prefix + ".up_conv.weight"], sd[prefix + ".up_conv.bias"], stride=2),
                  sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"], mk)
         xcat = torch.cat((u, skip), 1)
-        xcat = _gdr(F.conv3d(xcat, sd[prefix + ".conv.weight"], sd[prefix + ".conv.bias"]),
+        xcat = _gdr(conv3d(xcat, sd[prefix + ".conv.weight"], sd[prefix + ".conv.bias"]),
                     sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"], mk)
         return lu_stack(prefix, xcat, n) + xcat
 
@@ -205,7 +209,7 @@ def vnet3d_forward(sd: Dict[str, Tensor], x: Tensor, masks: Optional[Sequence[Te
     out = up("up_tr128", out, out64, 3)
     out = up("up_tr64", out, out32, 2)
     out = up("up_tr32", out, out16, 1)
-    logits = F.conv3d(out, sd["out_tr.conv.weight"], sd["out_tr.conv.bias"])   # VNet3d.py:94
+    logits = conv3d(out, sd["out_tr.conv.weight"], sd["out_tr.conv.bias"])   # VNet3d.py:94
     if logits.shape[1] == 1:                                                     # VNet3d.py:95-98
         probs = torch.sigmoid(logits)
     else:

@@ -10,14 +10,19 @@ Host code is Python/PyTorch (device memory, streams, torch.distributed); every F
 hand-written CUDA kernels behind the C ABI of ``include/b200seg.h``.
 """
 from .runtime import (set_precision, get_precision, enable_data_parallel, disable_data_parallel)
-from .networks import VNet3d, UNet3d, UNet2d, initialize_weights
+from .networks import VNet3d, VNet2d, UNet3d, UNet2d, initialize_weights
 from .losses import (BinaryDiceLoss, BinaryCrossEntropyLoss, BinaryFocalLoss, BinaryCrossEntropyDiceLoss,
                      BinaryDiceFocalLoss, MutilCrossEntropyLoss, MutilFocalLoss, MutilDiceLoss,
                      MutilCrossEntropyDiceLoss)
 from .install import install, uninstall
 from .graphed import GraphedStep
+from .optim import FusedAdamW, FusedAdam
+from .metric import dice_coeff, iou_coeff, multiclass_dice_coeff, multiclass_iou_coeff
+from .inference import predict, predict_mask, sliding_window_mask
 
-__all__ = ["VNet3d", "UNet3d", "UNet2d", "initialize_weights", "set_precision", "get_precision",
+__all__ = ["VNet3d", "VNet2d", "UNet3d", "UNet2d", "initialize_weights", "FusedAdamW", "FusedAdam", "dice_coeff",
+           "iou_coeff", "multiclass_dice_coeff", "multiclass_iou_coeff", "predict", "predict_mask",
+           "sliding_window_mask", "set_precision", "get_precision",
            "enable_data_parallel", "disable_data_parallel", "install", "uninstall", "GraphedStep",
            "BinaryDiceLoss", "BinaryCrossEntropyLoss", "BinaryFocalLoss", "BinaryCrossEntropyDiceLoss",
            "BinaryDiceFocalLoss", "MutilCrossEntropyLoss", "MutilFocalLoss", "MutilDiceLoss",

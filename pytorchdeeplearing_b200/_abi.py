@@ -15,6 +15,7 @@ import torch
 
 K3, K1, DOWN, UP = 0, 1, 2, 3
 F32, BF16, BF16_TC, BF16_HALO, BF16_HALO_WS = 0, 1, 2, 3, 4
+I64 = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200seg.so")
@@ -71,9 +72,15 @@ _SIGNATURES = {
     "b200seg_head_fwd": ([_PT, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
     "b200seg_head_bwd_supported": ([_i, _i], C.c_int),
     "b200seg_head_bwd": ([_PT, _vp, _vp, _PT, _vp, _vp, _i, _i, _vp], C.c_int),
-    "b200seg_loss_partials": ([_vp, _vp, _i64, _i, _f, _f, _vp, _i, _vp], C.c_int),
+    "b200seg_loss_partials": ([_vp, _vp, _i, _i, _i64, _i, _f, _f, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_loss_finalize": ([_vp, _i, _i, _vp, _f, _f, _vp, _vp, _i, _vp], C.c_int),
-    "b200seg_loss_bwd": ([_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_loss_bwd": ([_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_metric_partials": ([_vp, _vp, _i, _i, _i64, _i, _f, _vp, _i, _vp], C.c_int),
+    "b200seg_metric_finalize": ([_vp, _i, _i, _vp, _i, _vp], C.c_int),
+    "b200seg_adam_step": ([_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _vp, _i, _i, _vp], C.c_int),
+    "b200seg_dropout_masks": ([_vp, _vp, _i, _i, C.c_double, _vp, _i, _vp], C.c_int),
+    "b200seg_head_mask": ([_PT, _vp, _vp, _vp, _i, _f, _i, _vp], C.c_int),
+    "b200seg_mask_logits": ([_vp, _i64, _i, _f, _vp, _i, _vp], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
@@ -99,7 +106,7 @@ def load_library(path: Optional[str] = None):
             fn = getattr(lib, name)          # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
             fn.restype = restype
-        if lib.b200seg_version() < 100:
+        if lib.b200seg_version() < 200:
             raise RuntimeError("libb200seg.so is older than the Python binding")
         if path is None:
             _lib = lib
@@ -427,7 +434,7 @@ class CudaBackend:
             return False
         dev, st = self._ds(x)
         dx = _desc(x)
-        self._check(self.lib.b200seg_head_fwd(C.byref(dx), w.data_ptr(), _p(bias), logits.data_ptr(), probs.data_ptr(),
+        self._check(self.lib.b200seg_head_fwd(C.byref(dx), w.data_ptr(), _p(bias), logits.data_ptr(), _p(probs),
                                               nc, dev, st))
         return True
 
@@ -441,11 +448,26 @@ class CudaBackend:
                                               dw.data_ptr(), db.data_ptr(), nc, dev, st))
         return True
 
-    def loss_partials(self, logits, labels, gamma, alpha_f, part):
+    @staticmethod
+    def _label_dtype(labels):
+        if labels.dtype == torch.int64:
+            return I64
+        if labels.dtype == torch.float32:
+            return F32
+        raise TypeError(f"labels must be int64 (or fp32 soft targets for the binary losses), got {labels.dtype}")
+
+    @staticmethod
+    def part_size(c):
+        """doubles in the loss partial-sum buffer (include/b200seg.h: b200seg_loss_partials)"""
+        return 3 * c + 4 if c > 1 else 7
+
+    def loss_partials(self, logits, labels, gamma, alpha_f, part, metric=None):
+        """logits (N, ..., C) fp32 channels-last contiguous; labels (N, ...) int64 / fp32; metric [N][C][3] fp64 or None"""
         dev, st = self._ds(logits)
-        c = logits.shape[-1]
-        self._check(self.lib.b200seg_loss_partials(logits.data_ptr(), labels.data_ptr(), logits.numel() // c, c,
-                                                   gamma, alpha_f, part.data_ptr(), dev, st))
+        n, c = logits.shape[0], logits.shape[-1]
+        self._check(self.lib.b200seg_loss_partials(logits.data_ptr(), labels.data_ptr(), self._label_dtype(labels), n,
+                                                   logits.numel() // (n * c), c, gamma, alpha_f, part.data_ptr(),
+                                                   _p(metric), dev, st))
 
     def loss_finalize(self, part, c, terms, alpha, gamma, alpha_f, loss, lcoef):
         dev, st = self._ds(part)
@@ -455,5 +477,73 @@ class CudaBackend:
     def loss_bwd(self, logits, labels, lcoef, gscale, dlogits):
         dev, st = self._ds(logits)
         c = logits.shape[-1]
-        self._check(self.lib.b200seg_loss_bwd(logits.data_ptr(), labels.data_ptr(), logits.numel() // c, c,
-                                              lcoef.data_ptr(), gscale.data_ptr(), dlogits.data_ptr(), dev, st))
+        self._check(self.lib.b200seg_loss_bwd(logits.data_ptr(), labels.data_ptr(), self._label_dtype(labels),
+                                              logits.numel() // c, c, lcoef.data_ptr(), gscale.data_ptr(),
+                                              dlogits.data_ptr(), dev, st))
+
+    # ------------------------------------------------------------------ per-step accuracy (model/metric.py)
+    def metric_partials(self, probs, labels, threshold, metric):
+        """probs (N, ..., C) fp32 channels-last contiguous; metric [N][C][3] fp64 (+=)"""
+        dev, st = self._ds(probs)
+        n, c = probs.shape[0], probs.shape[-1]
+        self._check(self.lib.b200seg_metric_partials(probs.data_ptr(), labels.data_ptr(), self._label_dtype(labels), n,
+                                                     probs.numel() // (n * c), c, threshold, metric.data_ptr(), dev, st))
+
+    def metric_finalize(self, metric, out):
+        dev, st = self._ds(metric)
+        n, c = metric.shape[0], metric.shape[1]
+        self._check(self.lib.b200seg_metric_finalize(metric.data_ptr(), n, c, out.data_ptr(), dev, st))
+
+    # ------------------------------------------------------------------ optimizer / dropout masks / inference head
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, state, lr, beta1, beta2, eps, weight_decay, decoupled,
+                  gscale=None, tick=True):
+        dev, st = self._ds(param)
+        self._check(self.lib.b200seg_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                                               exp_avg_sq.data_ptr(), param.numel(), state.data_ptr(), lr, beta1,
+                                               beta2, eps, weight_decay, 1 if decoupled else 0, _p(gscale),
+                                               1 if tick else 0, dev, st))
+        if tick:
+            self.launch_count += 1
+
+    def upload_bytes(self, raw: bytes, device):
+        """host bytes -> new device uint8 tensor through kernel arguments (b200seg_upload_table; no memcpy node)"""
+        pad = (len(raw) + 15) // 16 * 16
+        buf = (C.c_char * pad)()
+        C.memmove(buf, raw, len(raw))
+        devt = torch.empty(pad, dtype=torch.uint8, device=device)
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        self._check(self.lib.b200seg_upload_table(C.cast(buf, C.c_void_p), pad, devt.data_ptr(), dev,
+                                                  torch.cuda.current_stream(dev).cuda_stream))
+        return devt
+
+    def upload_into(self, raw: bytes, dst: torch.Tensor):
+        """host bytes -> EXISTING device tensor (len(raw) <= dst bytes, multiple of 16)"""
+        pad = (len(raw) + 15) // 16 * 16
+        buf = (C.c_char * pad)()
+        C.memmove(buf, raw, len(raw))
+        dev, st = self._ds(dst)
+        self._check(self.lib.b200seg_upload_table(C.cast(buf, C.c_void_p), pad, dst.data_ptr(), dev, st))
+
+    def dropout_masks(self, rng, table, nmasks, total, p_drop, out):
+        """rng: int64 [2] device {seed, offset}; table: int32 [nmasks][3] device {first, count, first element index
+        within the (global-batch) draw}; out fp32 [total]"""
+        dev, st = self._ds(out)
+        self._check(self.lib.b200seg_dropout_masks(rng.data_ptr(), table.data_ptr(), nmasks, total, p_drop,
+                                                   out.data_ptr(), dev, st))
+
+    def head_mask(self, x, w, bias, mask, threshold):
+        """x (N,D,H,W,Cin); mask uint8 (N,D,H,W). False if the fused path does not take the shape."""
+        nc = w.shape[0]
+        if nc > 8 or x.shape[-1] % 4 != 0:
+            return False
+        dev, st = self._ds(x)
+        dx = _desc(x)
+        self._check(self.lib.b200seg_head_mask(C.byref(dx), w.data_ptr(), _p(bias), mask.data_ptr(), nc, threshold,
+                                               dev, st))
+        return True
+
+    def mask_logits(self, logits, threshold, mask):
+        dev, st = self._ds(logits)
+        c = logits.shape[-1]
+        self._check(self.lib.b200seg_mask_logits(logits.data_ptr(), logits.numel() // c, c, threshold,
+                                                 mask.data_ptr(), dev, st))

@@ -99,11 +99,22 @@ int ew_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, in
 int ew_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* go, const b200seg_tensor* addend,
                 const b200seg_tensor* gx, int dims, int device, cudaStream_t s);
 int ew_head_probs(const float* logits, float* probs, long long nvox_, int C, int device, cudaStream_t s);
-int loss_partials(const float* logits, const long long* labels, long long nvox_, int C, float gamma, float alpha_f,
-                  double* part, int device, cudaStream_t s);
+int loss_partials(const float* logits, const void* labels, int label_dtype, int N, long long vox, int C, float gamma,
+                  float alpha_f, double* part, double* metric, int device, cudaStream_t s);
+int metric_partials(const float* probs, const void* labels, int label_dtype, int N, long long vox, int C, float thr,
+                    double* metric, int device, cudaStream_t s);
+int metric_finalize(const double* metric, int N, int C, float* out, cudaStream_t s);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float* state, float lr, float beta1,
+              float beta2, float eps, float wd, int decoupled, const float* gscale, int tick, int device,
+              cudaStream_t s);
+int dropout_masks(const long long* rng, const int* table, int nmasks, int total, double p_drop, float* out,
+                  cudaStream_t s);
+int head_mask(const b200seg_tensor* x, const float* w, const float* bias, unsigned char* mask, int nc, float thr,
+              int device, cudaStream_t st);
+int mask_logits(const float* logits, long long nv, int C, float thr, unsigned char* mask, int device, cudaStream_t st);
 int loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f, float* loss,
                   float* lcoef, cudaStream_t s);
-int loss_bwd(const float* logits, const long long* labels, long long nvox_, int C, const float* lcoef,
+int loss_bwd(const float* logits, const void* labels, int label_dtype, long long nvox_, int C, const float* lcoef,
              const float* gscale, float* dlogits, int device, cudaStream_t s);
 
 static bool valid_tensor(const b200seg_tensor* t) {
@@ -370,7 +381,7 @@ int b200seg_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* g_out, const
 int b200seg_head_fwd(const b200seg_tensor* x, const float* w, const float* bias, float* logits, float* probs, int nc,
                      int device, b200seg_stream stream) {
   REQ_TENSOR(x, "x");
-  B200_CHECK_ARG(w && logits && probs, "b200seg_head_fwd: null argument");
+  B200_CHECK_ARG(w && logits, "b200seg_head_fwd: null argument");
   B200_DEVICE(device);
   return head_fwd(x, w, bias, logits, probs, nc, device, ST(stream));
 }
@@ -396,12 +407,57 @@ int b200seg_head_probs(const float* logits, float* probs, int64_t nvox_, int C, 
   return ew_head_probs(logits, probs, nvox_, C, device, ST(stream));
 }
 
-int b200seg_loss_partials(const float* logits, const int64_t* labels, int64_t nvox_, int C, float gamma, float alpha_f,
-                          double* part, int device, b200seg_stream stream) {
-  B200_CHECK_ARG(logits && labels && part && nvox_ > 0, "b200seg_loss_partials: bad argument");
+int b200seg_loss_partials(const float* logits, const void* labels, int label_dtype, int N, int64_t vox, int C,
+                          float gamma, float alpha_f, double* part, double* metric, int device,
+                          b200seg_stream stream) {
+  B200_CHECK_ARG(logits && labels && part && vox > 0 && N > 0, "b200seg_loss_partials: bad argument");
   B200_DEVICE(device);
-  return loss_partials(logits, reinterpret_cast<const long long*>(labels), nvox_, C, gamma, alpha_f, part, device,
-                       ST(stream));
+  return loss_partials(logits, labels, label_dtype, N, vox, C, gamma, alpha_f, part, metric, device, ST(stream));
+}
+
+int b200seg_metric_partials(const float* probs, const void* labels, int label_dtype, int N, int64_t vox, int C,
+                            float threshold, double* metric, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(probs && labels && metric && vox > 0 && N > 0, "b200seg_metric_partials: bad argument");
+  B200_CHECK_ARG(label_dtype == B200SEG_I64 || label_dtype == B200SEG_F32, "b200seg_metric_partials: bad label dtype");
+  B200_DEVICE(device);
+  return metric_partials(probs, labels, label_dtype, N, vox, C, threshold, metric, device, ST(stream));
+}
+
+int b200seg_metric_finalize(const double* metric, int N, int C, float* out, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(metric && out && N > 0 && C > 0, "b200seg_metric_finalize: bad argument");
+  B200_DEVICE(device);
+  return metric_finalize(metric, N, C, out, ST(stream));
+}
+
+int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                      const float* gscale, int tick, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && state && n > 0, "b200seg_adam_step: bad argument");
+  B200_DEVICE(device);
+  return adam_step(param, grad, exp_avg, exp_avg_sq, n, state, lr, beta1, beta2, eps, weight_decay, decoupled, gscale,
+                   tick, device, ST(stream));
+}
+
+int b200seg_dropout_masks(const int64_t* rng, const int32_t* table, int nmasks, int total, double p_drop, float* out,
+                          int device, b200seg_stream stream) {
+  B200_CHECK_ARG(rng && table && out, "b200seg_dropout_masks: null argument");
+  B200_DEVICE(device);
+  return dropout_masks(reinterpret_cast<const long long*>(rng), table, nmasks, total, p_drop, out, ST(stream));
+}
+
+int b200seg_head_mask(const b200seg_tensor* x, const float* w, const float* bias, uint8_t* mask, int nc,
+                      float threshold, int device, b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  B200_CHECK_ARG(w && mask, "b200seg_head_mask: null argument");
+  B200_DEVICE(device);
+  return head_mask(x, w, bias, mask, nc, threshold, device, ST(stream));
+}
+
+int b200seg_mask_logits(const float* logits, int64_t nvox_, int C, float threshold, uint8_t* mask, int device,
+                        b200seg_stream stream) {
+  B200_CHECK_ARG(logits && mask && nvox_ > 0 && C > 0, "b200seg_mask_logits: bad argument");
+  B200_DEVICE(device);
+  return mask_logits(logits, nvox_, C, threshold, mask, device, ST(stream));
 }
 
 int b200seg_loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f,
@@ -412,12 +468,11 @@ int b200seg_loss_finalize(const double* part, int C, int terms, const float* alp
   return loss_finalize(part, C, terms, alpha, gamma, alpha_f, loss, lcoef, ST(stream));
 }
 
-int b200seg_loss_bwd(const float* logits, const int64_t* labels, int64_t nvox_, int C, const float* lcoef,
-                     const float* gscale, float* dlogits, int device, b200seg_stream stream) {
+int b200seg_loss_bwd(const float* logits, const void* labels, int label_dtype, int64_t nvox_, int C,
+                     const float* lcoef, const float* gscale, float* dlogits, int device, b200seg_stream stream) {
   B200_CHECK_ARG(logits && labels && lcoef && gscale && dlogits && nvox_ > 0, "b200seg_loss_bwd: bad argument");
   B200_DEVICE(device);
-  return loss_bwd(logits, reinterpret_cast<const long long*>(labels), nvox_, C, lcoef, gscale, dlogits, device,
-                  ST(stream));
+  return loss_bwd(logits, labels, label_dtype, nvox_, C, lcoef, gscale, dlogits, device, ST(stream));
 }
 
 }  // extern "C"

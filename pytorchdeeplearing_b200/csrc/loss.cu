@@ -2,7 +2,12 @@
 // partial sum the Dice / BCE / CE / focal family needs, a scalar finalize, and ONE elementwise
 // backward pass writing d loss / d logits (closed forms: SURVEY.md App. C; reference formulas:
 // model/losses.py:43-53,141-147,160-181,252-260,273-285,301-325).
-// logits: fp32 channels-last [nvox][C]; labels: int64 [nvox] (read as-is, 8 B/voxel).
+// logits: fp32 channels-last [N][vox][C]; labels: int64 [N][vox] (read as-is, 8 B/voxel); the binary losses also
+// take fp32 soft targets (``y_true.float()``, model/losses.py:47,144).
+// The same pass also produces (optionally) the per-sample sums of the reference's per-step accuracy
+// (model/metric.py:146-181 dice_coeff / iou_coeff / multiclass_dice_coeff on the thresholded probabilities), so the
+// training step needs no separate read of ``probs`` for it, and counts labels outside [0, C) (the reference raises
+// in F.one_hot / F.cross_entropy; here the count lands in ``part`` and the host raises).
 #include "common.cuh"
 
 namespace b200seg {
@@ -25,17 +30,21 @@ __device__ __forceinline__ double block_reduce_to_global(double v, double* dst, 
 
 __device__ __forceinline__ float softplus_neg_abs(float z) { return log1pf(expf(-fabsf(z))); }
 
-// ---- binary (C == 1): I = sum p t, P = sum p, T = sum t, sum bce, sum alpha (1-pt)^gamma bce, V
+// ---- binary (C == 1): I = sum p t, P = sum p, T = sum t, sum bce, sum alpha (1-pt)^gamma bce, V, bad
+// grid = (blocks per sample, N); metric[n][0] = {sum [p>.5] t, sum [p>.5], sum t}
+template <typename TL>
 __global__ void __launch_bounds__(256) loss_partials_binary_kernel(const float* __restrict__ z,
-                                                                   const long long* __restrict__ t, long long nvox,
+                                                                   const TL* __restrict__ t, long long vox,
                                                                    float gamma, float alpha_f,
-                                                                   double* __restrict__ part) {
+                                                                   double* __restrict__ part,
+                                                                   double* __restrict__ metric) {
   __shared__ double s_tmp[8];
-  float aI = 0.f, aP = 0.f, aT = 0.f, aB = 0.f, aF = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
+  const long long base = (long long)blockIdx.y * vox;
+  float aI = 0.f, aP = 0.f, aT = 0.f, aB = 0.f, aF = 0.f, mI = 0.f, mA = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vox;
        i += (long long)gridDim.x * blockDim.x) {
-    float zi = z[i];
-    float ti = (float)t[i];
+    float zi = z[base + i];
+    float ti = (float)t[base + i];
     float p = 1.f / (1.f + expf(-zi));
     float b = fmaxf(zi, 0.f) - zi * ti + softplus_neg_abs(zi);
     float pt = expf(-b);
@@ -44,27 +53,41 @@ __global__ void __launch_bounds__(256) loss_partials_binary_kernel(const float* 
     aT += ti;
     aB += b;
     aF += alpha_f * powf(1.f - pt, gamma) * b;
+    if (p > 0.5f) {
+      mI += ti;
+      mA += 1.f;
+    }
   }
   block_reduce_to_global((double)aI, part + 0, s_tmp);
   block_reduce_to_global((double)aP, part + 1, s_tmp);
   block_reduce_to_global((double)aT, part + 2, s_tmp);
   block_reduce_to_global((double)aB, part + 3, s_tmp);
   block_reduce_to_global((double)aF, part + 4, s_tmp);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 5, (double)nvox);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 5, (double)vox);
+  if (metric != nullptr) {
+    double* m = metric + (long long)blockIdx.y * 3;
+    block_reduce_to_global((double)mI, m + 0, s_tmp);
+    block_reduce_to_global((double)mA, m + 1, s_tmp);
+    block_reduce_to_global((double)aT, m + 2, s_tmp);
+  }
 }
 
-// ---- multi-class, C <= kMaxC in registers
+// ---- multi-class, C <= kMaxC in registers; grid = (blocks per sample, N)
+// metric[n][c] = {sum [p_c>.5][t==c], sum [p_c>.5], sum [t==c]}; part[3C+3] += labels outside [0, C)
 template <int C>
 __global__ void __launch_bounds__(256) loss_partials_multi_kernel(const float* __restrict__ z,
-                                                                  const long long* __restrict__ t, long long nvox,
-                                                                  float gamma, double* __restrict__ part) {
+                                                                  const long long* __restrict__ t, long long vox,
+                                                                  float gamma, double* __restrict__ part,
+                                                                  double* __restrict__ metric) {
   __shared__ double s_tmp[8];
-  float aI[C], aP[C], aN[C];
-  float aNll = 0.f, aF = 0.f;
+  const long long base = (long long)blockIdx.y * vox;
+  float aI[C], aP[C], aN[C], mI[C], mA[C];
+  float aNll = 0.f, aF = 0.f, aBad = 0.f;
 #pragma unroll
-  for (int c = 0; c < C; ++c) aI[c] = aP[c] = aN[c] = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (int c = 0; c < C; ++c) aI[c] = aP[c] = aN[c] = mI[c] = mA[c] = 0.f;
+  for (long long ii = blockIdx.x * (long long)blockDim.x + threadIdx.x; ii < vox;
+       ii += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + ii;
     float v[C];
     if (C == 2) {
       float2 q = *reinterpret_cast<const float2*>(z + i * 2);
@@ -76,7 +99,12 @@ __global__ void __launch_bounds__(256) loss_partials_multi_kernel(const float* _
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] = z[i * C + c];
     }
-    const int ti = (int)t[i];
+    const long long tl = t[i];
+    if (tl < 0 || tl >= C) {          // the reference raises (F.one_hot / F.cross_entropy); flagged for the host
+      aBad += 1.f;
+      continue;
+    }
+    const int ti = (int)tl;
     float mx = v[0];
 #pragma unroll
     for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c]);
@@ -93,11 +121,14 @@ __global__ void __launch_bounds__(256) loss_partials_multi_kernel(const float* _
     for (int c = 0; c < C; ++c) {
       const float p = e[c] * inv;
       const bool hit = (c == ti);
+      const bool on = p > 0.5f;
       aP[c] += p;
+      if (on) mA[c] += 1.f;
       if (hit) {
         aI[c] += p;
         aN[c] += 1.f;
         zt = v[c];
+        if (on) mI[c] += 1.f;
       }
     }
     const float nll = lse - zt;
@@ -113,21 +144,43 @@ __global__ void __launch_bounds__(256) loss_partials_multi_kernel(const float* _
   }
   block_reduce_to_global((double)aNll, part + 3 * C, s_tmp);
   block_reduce_to_global((double)aF, part + 3 * C + 1, s_tmp);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 3 * C + 2, (double)nvox);
+  block_reduce_to_global((double)aBad, part + 3 * C + 3, s_tmp);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 3 * C + 2, (double)vox);
+  if (metric != nullptr) {
+    double* m = metric + (long long)blockIdx.y * C * 3;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      block_reduce_to_global((double)mI[c], m + 3 * c + 0, s_tmp);
+      block_reduce_to_global((double)mA[c], m + 3 * c + 1, s_tmp);
+      block_reduce_to_global((double)aN[c], m + 3 * c + 2, s_tmp);
+    }
+  }
 }
 
 // ---- multi-class, any C (<= 1024): per-class sums through shared-memory atomics
 __global__ void __launch_bounds__(256) loss_partials_multi_generic_kernel(const float* __restrict__ z,
                                                                           const long long* __restrict__ t,
-                                                                          long long nvox, int C, float gamma,
-                                                                          double* __restrict__ part) {
-  extern __shared__ float s_acc[];   // [3*C + 2]
-  for (int i = threadIdx.x; i < 3 * C + 2; i += blockDim.x) s_acc[i] = 0.f;
+                                                                          long long vox, int C, float gamma,
+                                                                          double* __restrict__ part,
+                                                                          double* __restrict__ metric) {
+  extern __shared__ float s_acc[];   // [3*C + 2] loss sums, [1] bad labels, [2*C] metric
+  const int NS = 5 * C + 3;
+  for (int i = threadIdx.x; i < NS; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
-       i += (long long)gridDim.x * blockDim.x) {
+  float* s_bad = s_acc + 3 * C + 2;
+  float* s_mI = s_bad + 1;
+  float* s_mA = s_mI + C;
+  const long long base = (long long)blockIdx.y * vox;
+  for (long long ii = blockIdx.x * (long long)blockDim.x + threadIdx.x; ii < vox;
+       ii += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + ii;
     const float* zi = z + i * C;
-    const int ti = (int)t[i];
+    const long long tl = t[i];
+    if (tl < 0 || tl >= C) {
+      atomicAdd(s_bad, 1.f);
+      continue;
+    }
+    const int ti = (int)tl;
     float mx = zi[0];
     for (int c = 1; c < C; ++c) mx = fmaxf(mx, zi[c]);
     float s = 0.f;
@@ -136,9 +189,11 @@ __global__ void __launch_bounds__(256) loss_partials_multi_generic_kernel(const 
     for (int c = 0; c < C; ++c) {
       const float p = expf(zi[c] - mx) * inv;
       atomicAdd(&s_acc[C + c], p);
+      if (p > 0.5f) atomicAdd(&s_mA[c], 1.f);
       if (c == ti) {
         atomicAdd(&s_acc[c], p);
         atomicAdd(&s_acc[2 * C + c], 1.f);
+        if (p > 0.5f) atomicAdd(&s_mI[c], 1.f);
       }
     }
     const float nll = lse - zi[ti];
@@ -147,7 +202,76 @@ __global__ void __launch_bounds__(256) loss_partials_multi_generic_kernel(const 
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * C + 2; i += blockDim.x) atomicAdd(part + i, (double)s_acc[i]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 3 * C + 2, (double)nvox);
+  if (threadIdx.x == 0 && s_bad[0] != 0.f) atomicAdd(part + 3 * C + 3, (double)s_bad[0]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(part + 3 * C + 2, (double)vox);
+  if (metric != nullptr) {
+    double* m = metric + (long long)blockIdx.y * C * 3;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(m + 3 * c + 0, (double)s_mI[c]);
+      atomicAdd(m + 3 * c + 1, (double)s_mA[c]);
+      atomicAdd(m + 3 * c + 2, (double)s_acc[2 * C + c]);
+    }
+  }
+}
+
+// ---- per-step accuracy from the per-sample sums (model/metric.py:146-181): out[0] = dice_coeff (C == 1) or
+// multiclass_dice_coeff (mean over classes 1..C-1 of the per-sample-mean Dice), out[1] = the iou_coeff analogue
+__global__ void metric_finalize_kernel(const double* __restrict__ metric, int N, int C, float* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double s = 1e-5;
+  double dice = 0.0, iou = 0.0;
+  const int c0 = C == 1 ? 0 : 1;
+  for (int c = c0; c < C; ++c) {
+    double dc = 0.0, ic = 0.0;
+    for (int n = 0; n < N; ++n) {
+      const double* m = metric + ((long long)n * C + c) * 3;
+      dc += (2.0 * m[0] + s) / (m[1] + m[2] + s);
+      ic += (m[0] + s) / (m[1] + m[2] - m[0] + s);
+    }
+    dice += dc / N;
+    iou += ic / N;
+  }
+  const int nc = C == 1 ? 1 : C - 1;
+  out[0] = (float)(dice / nc);
+  out[1] = (float)(iou / nc);
+}
+
+// ---- the same per-sample sums from materialised probabilities (drop-in dice_coeff(probs, y) etc.): probs fp32
+// channels-last [N][vox][C]; labels int64 or fp32 (C == 1 only)
+template <typename TL>
+__global__ void __launch_bounds__(256) metric_partials_kernel(const float* __restrict__ p, const TL* __restrict__ t,
+                                                              long long vox, int C, float thr,
+                                                              double* __restrict__ metric) {
+  extern __shared__ float s_m[];     // [3*C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_m[i] = 0.f;
+  __syncthreads();
+  const long long base = (long long)blockIdx.y * vox;
+  for (long long ii = blockIdx.x * (long long)blockDim.x + threadIdx.x; ii < vox;
+       ii += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + ii;
+    if (C == 1) {
+      const float ti = (float)t[i];
+      const bool on = p[i] > thr;
+      if (on) {
+        atomicAdd(&s_m[0], ti);
+        atomicAdd(&s_m[1], 1.f);
+      }
+      if (ti != 0.f) atomicAdd(&s_m[2], ti);
+    } else {
+      const long long tl = (long long)t[i];
+      for (int c = 0; c < C; ++c) {
+        const bool on = p[i * C + c] > thr;
+        const bool hit = tl == c;
+        if (on) atomicAdd(&s_m[3 * c + 1], 1.f);
+        if (hit) atomicAdd(&s_m[3 * c + 2], 1.f);
+        if (on && hit) atomicAdd(&s_m[3 * c + 0], 1.f);
+      }
+    }
+  }
+  __syncthreads();
+  double* m = metric + (long long)blockIdx.y * C * 3;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x)
+    if (s_m[i] != 0.f) atomicAdd(m + i, (double)s_m[i]);
 }
 
 // ---- finalize: one thread
@@ -202,6 +326,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ part, int C, int
     lcoef[2 * C] = (terms & B200SEG_LOSS_CE) ? (float)(1.0 / V) : 0.f;
     lcoef[2 * C + 1] = (terms & B200SEG_LOSS_FOCAL) ? (float)(1.0 / V) : 0.f;
     lcoef[2 * C + 2] = gamma;
+    if (part[3 * C + 3] > 0.0) val = __longlong_as_double(0x7ff8000000000000LL);   // labels outside [0, C)
   }
   loss[0] = (float)val;
 }
@@ -215,8 +340,9 @@ __device__ __forceinline__ float focal_factor(float ce, float gamma) {
   return powf(om, gamma) + gamma * powf(om, gamma - 1.f) * pt * ce;
 }
 
+template <typename TL>
 __global__ void __launch_bounds__(256) loss_bwd_binary_kernel(const float* __restrict__ z,
-                                                              const long long* __restrict__ t, long long nvox,
+                                                              const TL* __restrict__ t, long long nvox,
                                                               const float* __restrict__ lcoef,
                                                               const float* __restrict__ gscale,
                                                               float* __restrict__ dz) {
@@ -299,7 +425,12 @@ __global__ void __launch_bounds__(256) loss_bwd_multi_generic_kernel(const float
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
        i += (long long)gridDim.x * blockDim.x) {
     const float* zi = z + i * C;
-    const int ti = (int)t[i];
+    const long long tl = t[i];
+    if (tl < 0 || tl >= C) {             // flagged by loss_partials (the host raises): no out-of-bounds read
+      for (int c = 0; c < C; ++c) dz[i * C + c] = 0.f;
+      continue;
+    }
+    const int ti = (int)tl;
     float mx = zi[0];
     for (int c = 1; c < C; ++c) mx = fmaxf(mx, zi[c]);
     float s = 0.f;
@@ -328,23 +459,62 @@ static int loss_blocks(long long nvox_, int device) {
   return (int)blocks;
 }
 
-int loss_partials(const float* logits, const long long* labels, long long nvox_, int C, float gamma, float alpha_f,
-                  double* part, int device, cudaStream_t s) {
+// blocks per sample for the (blocks, N) grids of the partial-sum kernels
+static dim3 sample_grid(long long vox, int N, int device) {
+  long long per = (vox + 256 * 4 - 1) / (256 * 4);
+  long long cap = ((long long)num_sms(device) * 8 + N - 1) / N;
+  if (per > cap) per = cap;
+  if (per < 1) per = 1;
+  return dim3((unsigned)per, (unsigned)N, 1);
+}
+
+int loss_partials(const float* logits, const void* labels, int label_dtype, int N, long long vox, int C, float gamma,
+                  float alpha_f, double* part, double* metric, int device, cudaStream_t s) {
   B200_CHECK_ARG(C >= 1 && C <= 1024, "loss_partials: unsupported class count %d", C);
-  const int blocks = loss_blocks(nvox_, device);
+  B200_CHECK_ARG(N >= 1 && N <= 65535, "loss_partials: unsupported batch size %d", N);
+  B200_CHECK_ARG(label_dtype == B200SEG_I64 || (label_dtype == B200SEG_F32 && C == 1),
+                 "loss_partials: labels must be int64 (fp32 soft targets only for the binary losses)");
+  const dim3 grid = sample_grid(vox, N, device);
+  const long long* tl = static_cast<const long long*>(labels);
   switch (C) {
-    case 1: loss_partials_binary_kernel<<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, alpha_f, part); break;
-    case 2: loss_partials_multi_kernel<2><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
-    case 3: loss_partials_multi_kernel<3><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
-    case 4: loss_partials_multi_kernel<4><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
-    case 5: loss_partials_multi_kernel<5><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
-    case 6: loss_partials_multi_kernel<6><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
-    case 7: loss_partials_multi_kernel<7><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
-    case 8: loss_partials_multi_kernel<8><<<blocks, 256, 0, s>>>(logits, labels, nvox_, gamma, part); break;
+    case 1:
+      if (label_dtype == B200SEG_F32)
+        loss_partials_binary_kernel<float><<<grid, 256, 0, s>>>(logits, static_cast<const float*>(labels), vox, gamma,
+                                                                alpha_f, part, metric);
+      else
+        loss_partials_binary_kernel<long long><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, alpha_f, part, metric);
+      break;
+    case 2: loss_partials_multi_kernel<2><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 3: loss_partials_multi_kernel<3><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 4: loss_partials_multi_kernel<4><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 5: loss_partials_multi_kernel<5><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 6: loss_partials_multi_kernel<6><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 7: loss_partials_multi_kernel<7><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 8: loss_partials_multi_kernel<8><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
     default:
-      loss_partials_multi_generic_kernel<<<blocks, 256, (3 * C + 2) * sizeof(float), s>>>(logits, labels, nvox_, C,
-                                                                                          gamma, part);
+      loss_partials_multi_generic_kernel<<<grid, 256, (5 * C + 3) * sizeof(float), s>>>(logits, tl, vox, C, gamma,
+                                                                                        part, metric);
   }
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int metric_partials(const float* probs, const void* labels, int label_dtype, int N, long long vox, int C, float thr,
+                    double* metric, int device, cudaStream_t s) {
+  B200_CHECK_ARG(C >= 1 && C <= 1024 && N >= 1 && N <= 65535, "metric_partials: unsupported shape");
+  const dim3 grid = sample_grid(vox, N, device);
+  if (label_dtype == B200SEG_F32)
+    metric_partials_kernel<float><<<grid, 256, 3 * C * sizeof(float), s>>>(probs, static_cast<const float*>(labels),
+                                                                           vox, C, thr, metric);
+  else
+    metric_partials_kernel<long long><<<grid, 256, 3 * C * sizeof(float), s>>>(
+        probs, static_cast<const long long*>(labels), vox, C, thr, metric);
+  B200_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int metric_finalize(const double* metric, int N, int C, float* out, cudaStream_t s) {
+  metric_finalize_kernel<<<1, 32, 0, s>>>(metric, N, C, out);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -356,12 +526,21 @@ int loss_finalize(const double* part, int C, int terms, const float* alpha, floa
   return B200SEG_OK;
 }
 
-int loss_bwd(const float* logits, const long long* labels, long long nvox_, int C, const float* lcoef,
+int loss_bwd(const float* logits, const void* labels_, int label_dtype, long long nvox_, int C, const float* lcoef,
              const float* gscale, float* dlogits, int device, cudaStream_t s) {
   B200_CHECK_ARG(C >= 1 && C <= 1024, "loss_bwd: unsupported class count %d", C);
+  B200_CHECK_ARG(label_dtype == B200SEG_I64 || (label_dtype == B200SEG_F32 && C == 1),
+                 "loss_bwd: labels must be int64 (fp32 soft targets only for the binary losses)");
   const int blocks = loss_blocks(nvox_, device);
+  const long long* labels = static_cast<const long long*>(labels_);
   switch (C) {
-    case 1: loss_bwd_binary_kernel<<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 1:
+      if (label_dtype == B200SEG_F32)
+        loss_bwd_binary_kernel<float><<<blocks, 256, 0, s>>>(logits, static_cast<const float*>(labels_), nvox_, lcoef,
+                                                             gscale, dlogits);
+      else
+        loss_bwd_binary_kernel<long long><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits);
+      break;
     case 2: loss_bwd_multi_kernel<2><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
     case 3: loss_bwd_multi_kernel<3><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
     case 4: loss_bwd_multi_kernel<4><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;

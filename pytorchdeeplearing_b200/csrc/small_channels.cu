@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const TX* __restrict__ x,
       for (int c = 0; c < NC; ++c) p[c] *= inv;
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      logits[v * NC + c] = z[c];
-      probs[v * NC + c] = p[c];
+    for (int c = 0; c < NC; ++c) logits[v * NC + c] = z[c];
+    if (probs != nullptr) {           // a captured training step that reads the accuracy from the loss pass skips it
+#pragma unroll
+      for (int c = 0; c < NC; ++c) probs[v * NC + c] = p[c];
     }
   }
 }

@@ -112,6 +112,11 @@ class Engine:
         self._z32 = None
         self._packs: Dict[Tuple[str, str], object] = {}
         self._unpack_list: List[Tuple[Tensor, Tensor]] = []
+        self.bucket_hook = None                # data parallel: callable(flat, offset) when flat[offset:] is final
+        self._flat = None
+        self._goff: Dict[str, int] = {}
+        self.want_probs = True                 # False: the head writes logits only (GraphedStep: nobody reads probs)
+        self.mask_threshold: Optional[float] = None   # not None: inference head -> uint8 mask, no logits / probs
         self._side = None                      # side stream carrying this pass's weight gradients (if any)
         self._side_keep: List[object] = []     # operands of side-stream kernels stay referenced until the join
 
@@ -154,11 +159,25 @@ class Engine:
                 keys.append((wname, "dgrad"))
         self._packs = dict(zip(keys, self.be.pack_many(reqs)))
 
-    def _finish_backward(self) -> None:
+    def _join_side(self) -> None:
         if self._side is not None:
             torch.cuda.current_stream(self._side.device).wait_stream(self._side)
             self._side = None
         self._side_keep = []
+
+    def _flush_bucket(self, first_name: str) -> None:
+        """Data parallel: every gradient from parameter ``first_name`` to the end of the state_dict
+        (the deepest encoder block, the whole decoder and the head = what backward has finished so far) is final ->
+        unpack those weight gradients now and let the caller start their all-reduce under the rest of backward."""
+        if self.bucket_hook is None:
+            return
+        self._join_side()
+        self.be.unpack_many(self._unpack_list)
+        self._unpack_list = []
+        self.bucket_hook(self._flat, self._goff[first_name])
+
+    def _finish_backward(self) -> None:
+        self._join_side()
         self.be.unpack_many(self._unpack_list)
         self._unpack_list = []
         self._packs = {}
@@ -185,8 +204,9 @@ class Engine:
         vox = 1
         for s in out_sp:
             vox *= s
-        if getattr(self.be, "fused_gn", False):
+        if getattr(self.be, "fused_gn", False) and cout <= 512:
             # kernels derive the coefficients from the statistics themselves: no finalize launch
+            # (wider layers -- init_features >= 64 -- take the finalize/apply form: any channel count)
             L.gn = (stats, self.P[gname + ".weight"], self.P[gname + ".bias"], L.scale, vox, GROUPS, GN_EPS)
         else:
             L.coef = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
@@ -196,14 +216,23 @@ class Engine:
         self.layers.append(L)
         return L
 
-    def head(self, wname: str, bname: str, x: Tensor, sp0, ncls: int) -> Tuple[Layer, Tensor, Tensor]:
-        """OutputTransition3d / UNet head: 1x1 conv to the classes + sigmoid/softmax (VNet3d.py:90-99)."""
+    def head(self, wname: str, bname: str, x: Tensor, sp0, ncls: int) -> Tuple[Layer, Tensor, Optional[Tensor]]:
+        """OutputTransition3d / UNet head: 1x1 conv to the classes + sigmoid/softmax (VNet3d.py:90-99).
+        Inference form (``mask_threshold`` set; predict, model/modelVNet.py:655-676): the uint8 mask directly."""
+        if self.mask_threshold is not None:
+            mask = torch.empty((x.shape[0],) + tuple(sp0), dtype=torch.uint8, device=x.device)
+            if not self.be.head_mask(x, self.P[wname], self.P[bname], mask, float(self.mask_threshold)):
+                logits = self.new(x, sp0, ncls, dtype=torch.float32)
+                self.conv_raw(K1, wname, bname, x, logits)
+                self.be.mask_logits(logits, float(self.mask_threshold), mask)
+            return None, mask, None
         logits = self.new(x, sp0, ncls, dtype=torch.float32)
-        probs = torch.empty_like(logits)
+        probs = torch.empty_like(logits) if self.want_probs else None
         Lh = Layer(K1, wname, bname, None, x=x, y=logits)
         if not self.be.head_fwd(x, self.P[wname], self.P[bname], logits, probs):
             self.conv_raw(K1, wname, bname, x, logits)
-            self.be.head_probs(logits, probs)
+            if probs is not None:
+                self.be.head_probs(logits, probs)
         return Lh, logits, probs
 
     def head_backward(self, Lh: Layer, g_logits: Tensor) -> Tensor:
@@ -297,29 +326,46 @@ class Engine:
         total = sum(p.numel() for p in self.P.values())
         flat = torch.zeros(total, dtype=torch.float32, device=device)
         off = 0
-        self.grads = {}
+        self.grads, self._goff, self._flat = {}, {}, flat
         for name, p in self.P.items():
             self.grads[name] = flat[off:off + p.numel()].view(p.shape)
+            self._goff[name] = off
             off += p.numel()
         return flat
 
     # ================================================================== VNet3d
-    def vnet3d_forward(self, P: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]],
-                       need_grad: bool) -> Tuple[Tensor, Tensor]:
-        """VNet3d.forward (reference networks/VNet3d.py:129-158).  ``x``: (N,Cin,D,H,W) fp32.
-        Returns channels-last-strided (N,ncls,D,H,W) fp32 logits and probs."""
+    def _out_views(self, logits: Tensor, probs: Optional[Tensor]):
+        """(N,D,H,W,C) channels-last buffers -> the NCDHW / NCHW-shaped (channels-last-strided) tensors of the
+        nn.Module contract; a uint8 inference mask (N,D,H,W) loses the unit depth of the 2-D nets."""
+        if logits.dtype == torch.uint8:
+            return (logits if self.dims == 3 else logits[:, 0]), None
+        if self.dims == 3:
+            return logits.permute(0, 4, 1, 2, 3), (probs.permute(0, 4, 1, 2, 3) if probs is not None else None)
+        return logits[:, 0].permute(0, 3, 1, 2), (probs[:, 0].permute(0, 3, 1, 2) if probs is not None else None)
+
+    def vnet_forward(self, P: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]],
+                     need_grad: bool) -> Tuple[Tensor, Tensor]:
+        """VNet3d.forward (reference networks/VNet3d.py:129-158) and its 2-D twin VNet2d.forward
+        (networks/VNet2d.py:129-158; 2-D tensors run with a unit depth).  ``x``: (N,Cin,[D,]H,W) fp32.
+        Returns channels-last-strided (N,ncls,[D,]H,W) fp32 logits and probs."""
         self.P, self.masks, self._mi, self.layers, self.need_grad = P, masks, 0, [], need_grad
         sv = self.saved = {}
+        dims = self.dims
         n, cin = x.shape[0], x.shape[1]
         self._begin_pass(n, x.device, backward=False)
-        sp0 = tuple(x.shape[2:])
-        xin = x.permute(0, 2, 3, 4, 1)
+        if dims == 3:
+            sp0 = tuple(x.shape[2:])
+            xin = x.permute(0, 2, 3, 4, 1)
+        else:
+            sp0 = (1,) + tuple(x.shape[2:])
+            xin = x.permute(0, 2, 3, 1).unsqueeze(1)
         if cin != 1:
             xin = xin.contiguous()
         f = P["in_tr.conv1.weight"].shape[0]
         sps = [sp0]
         for _ in range(4):
-            sps.append(tuple(s // 2 for s in sps[-1]))
+            s_ = sps[-1]
+            sps.append((s_[0] // 2 if dims == 3 else 1, s_[1] // 2, s_[2] // 2))
         ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
         # skip-concat buffers of the four UpTransitions: [up | skip], VNet3d.py:74
         cats = [self.new(x, sps[i], 2 * ch[i]) for i in range(4)]
@@ -384,9 +430,11 @@ class Engine:
         ncls = P["out_tr.conv.weight"].shape[0]
         Lh, logits, probs = self.head("out_tr.conv.weight", "out_tr.conv.bias", out, sp0, ncls)
         sv["head"] = Lh
-        return logits.permute(0, 4, 1, 2, 3), probs.permute(0, 4, 1, 2, 3)
+        return self._out_views(logits, probs)
 
-    def vnet3d_backward(self, g_logits: Tensor) -> Tensor:
+    vnet3d_forward = vnet_forward
+
+    def vnet_backward(self, g_logits: Tensor) -> Tensor:
         """Gradients of all 128 parameters given d loss / d logits ((N,D,H,W,ncls) fp32,
         channels-last).  Returns the flat fp32 bucket; ``self.grads`` holds the views."""
         sv = self.saved
@@ -411,11 +459,15 @@ class Engine:
             for j in reversed(range(len(ops))):
                 gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None)
             g = self.bwd_layer(Ld, gh, True, dx_addend=gskip[i])
+            if i == 3:
+                self._flush_bucket("down_tr256.down_conv.weight")
         La, Lb = sv["in_tr"]
         self.bwd_layer(La, g, False)
         self.bwd_layer(Lb, g, False)
         self._finish_backward()
         return flat
+
+    vnet3d_backward = vnet_backward
 
     # ================================================================== UNet3d / UNet2d
     def unet_forward(self, P: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]],
@@ -479,9 +531,7 @@ class Engine:
         ncls = P["conv.weight"].shape[0]
         Lh, logits, probs = self.head("conv.weight", "conv.bias", h, sp0, ncls)
         sv["head"] = Lh
-        if dims == 3:
-            return logits.permute(0, 4, 1, 2, 3), probs.permute(0, 4, 1, 2, 3)
-        return logits[:, 0].permute(0, 3, 1, 2), probs[:, 0].permute(0, 3, 1, 2)
+        return self._out_views(logits, probs)
 
     def unet_backward(self, g_logits: Tensor) -> Tensor:
         sv = self.saved
@@ -499,6 +549,7 @@ class Engine:
             g = self.bwd_layer(sv[f"upconv{k}"], gcat[..., :co], True)
         L1, L2 = sv["bottleneck"]
         g = self.bwd_layer(L1, self.bwd_layer(L2, g, True), True)
+        self._flush_bucket("bottleneck.bottleneckconv1.weight")
         for i in (3, 2, 1, 0):
             e, pooled = sv[f"pool{i + 1}"]
             ge = torch.empty(e.shape, dtype=self.T, device=e.device)

@@ -4,6 +4,7 @@ from torch import nn
 from .Unet2d import UNet2d
 from .Unet3d import UNet3d
 from .VNet3d import VNet3d
+from .VNet2d import VNet2d
 
 
 def initialize_weights(net):
@@ -24,4 +25,4 @@ def initialize_weights(net):
         nn.init.constant_(net.bias.data, 0)
 
 
-__all__ = ["UNet2d", "UNet3d", "VNet3d", "initialize_weights"]
+__all__ = ["UNet2d", "UNet3d", "VNet3d", "VNet2d", "initialize_weights"]

@@ -63,6 +63,16 @@ def get_backend(t: torch.Tensor):
     return cuda_backend()
 
 
+def is_capturing(device=None) -> bool:
+    """True while the current CUDA stream is being captured into a graph (host-side checks that synchronise, and the
+    torch generator bookkeeping of the dropout masks, are skipped then)."""
+    if not torch.cuda.is_available():
+        return False
+    if device is not None and getattr(device, "type", "cuda") != "cuda":
+        return False
+    return torch.cuda.is_current_stream_capturing()
+
+
 # ---------------------------------------------------------------------------- data parallel
 _DP_GROUP = None
 _DP_ENABLED = False
@@ -86,3 +96,11 @@ def disable_data_parallel() -> None:
 
 def dp_state():
     return _DP_ENABLED, _DP_GROUP
+
+
+def dp_rank_world():
+    """(rank, world size) of the data-parallel group; (0, 1) when data parallelism is off."""
+    if not _DP_ENABLED:
+        return 0, 1
+    import torch.distributed as dist
+    return dist.get_rank(_DP_GROUP), dist.get_world_size(_DP_GROUP)

@@ -247,7 +247,8 @@ class EmuBackend:
         if bias is not None:
             z = z + bias.float()
         logits.copy_(z)
-        self.head_probs(logits, probs)
+        if probs is not None:
+            self.head_probs(logits, probs)
         return True
 
     def head_bwd(self, x, dlogits, w, dx, dw, db):
@@ -261,10 +262,16 @@ class EmuBackend:
         db += g.sum((0, 1, 2, 3)).float()
         return True
 
-    def loss_partials(self, logits, labels, gamma, alpha_f, part):
-        """part (double): multi-class C>1: [I_c]*C, [P_c]*C, [Cnt_c]*C, sum_nll, sum_focal, V
-                          binary  C==1: I, P, T, sum_bce, sum_focal(alpha folded), V"""
+    @staticmethod
+    def part_size(c):
+        return 3 * c + 4 if c > 1 else 7
+
+    def loss_partials(self, logits, labels, gamma, alpha_f, part, metric=None):
+        """part (double): multi-class C>1: [I_c]*C, [P_c]*C, [Cnt_c]*C, sum_nll, sum_focal, V, BAD
+                          binary  C==1: I, P, T, sum_bce, sum_focal(alpha folded), V, BAD
+        metric (double [N][C][3], optional): per sample/class {sum [p>.5][t==c], sum [p>.5], sum [t==c]}"""
         c = logits.shape[-1]
+        n = logits.shape[0]
         z = logits.reshape(-1, c).double()
         t = labels.reshape(-1)
         if c == 1:
@@ -275,9 +282,19 @@ class EmuBackend:
             vals = [(p * tf).sum(), p.sum(), tf.sum(), b.sum(), (alpha_f * (1 - pt) ** gamma * b).sum(),
                     torch.tensor(float(zf.numel()), dtype=torch.float64)]
             part[:6] += torch.stack(vals)
+            if metric is not None:
+                on = (torch.sigmoid(logits.reshape(n, -1).float()) > 0.5).double()
+                tn = labels.reshape(n, -1).double()
+                metric[:, 0, 0] += (on * tn).sum(1)
+                metric[:, 0, 1] += on.sum(1)
+                metric[:, 0, 2] += tn.sum(1)
         else:
+            bad = (t < 0) | (t >= c)
+            part[3 * c + 3] += float(bad.sum())
+            keep = ~bad
+            z, tk = z[keep], t[keep]
             p = torch.softmax(z, 1)
-            oh = F.one_hot(t.long(), c).double()
+            oh = F.one_hot(tk.long(), c).double()
             logp = torch.log_softmax(z, 1)
             nll = -(logp * oh).sum(1)
             ptt = torch.exp(-nll)
@@ -286,7 +303,66 @@ class EmuBackend:
             part[2 * c:3 * c] += oh.sum(0)
             part[3 * c] += nll.sum()
             part[3 * c + 1] += ((1 - ptt) ** gamma * nll).sum()
-            part[3 * c + 2] += float(z.shape[0])
+            part[3 * c + 2] += float(t.shape[0])
+            if metric is not None:
+                on = (torch.softmax(logits.reshape(n, -1, c).float(), -1) > 0.5).double()
+                ohn = F.one_hot(labels.reshape(n, -1).long().clamp(0, c - 1), c).double()
+                metric[..., 0] += (on * ohn).sum(1)
+                metric[..., 1] += on.sum(1)
+                metric[..., 2] += ohn.sum(1)
+
+    def metric_partials(self, probs, labels, threshold, metric):
+        n, c = probs.shape[0], probs.shape[-1]
+        on = (probs.reshape(n, -1, c) > threshold).double()
+        if c == 1:
+            tn = labels.reshape(n, -1, 1).double()
+        else:
+            tn = F.one_hot(labels.reshape(n, -1).long(), c).double()
+        metric[..., 0] += (on * tn).sum(1)
+        metric[..., 1] += on.sum(1)
+        metric[..., 2] += tn.sum(1)
+
+    def metric_finalize(self, metric, out):
+        n, c = metric.shape[0], metric.shape[1]
+        s = 1e-5
+        cls = [0] if c == 1 else list(range(1, c))
+        m = metric[:, cls]
+        dice = ((2 * m[..., 0] + s) / (m[..., 1] + m[..., 2] + s)).mean(0).mean()
+        iou = ((m[..., 0] + s) / (m[..., 1] + m[..., 2] - m[..., 0] + s)).mean(0).mean()
+        out[0], out[1] = dice.float(), iou.float()
+
+    def head_mask(self, x, w, bias, mask, threshold):
+        nc = w.shape[0]
+        if nc > 8 or x.shape[-1] % 4 != 0:
+            return False
+        z = torch.einsum("ndhwk,ck->ndhwc", x.float(), w.reshape(nc, -1).float())
+        if bias is not None:
+            z = z + bias.float()
+        self.mask_logits(z, threshold, mask)
+        return True
+
+    def mask_logits(self, logits, threshold, mask):
+        if logits.shape[-1] == 1:
+            mask.copy_(((torch.sigmoid(logits[..., 0]) > threshold) * 255).to(torch.uint8).reshape(mask.shape))
+        else:
+            mask.copy_(logits.argmax(-1).to(torch.uint8).reshape(mask.shape))
+
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, state, lr, beta1, beta2, eps, weight_decay, decoupled,
+                  gscale=None, tick=True):
+        if tick:
+            state[0] += 1
+            t = float(state[0])
+            state[1] = lr / (1 - beta1 ** t)
+            state[2] = (1 - beta2 ** t) ** 0.5
+        g = grad * (gscale if gscale is not None else 1.0)
+        if decoupled:
+            param.mul_(1 - lr * weight_decay)
+        else:
+            g = g + weight_decay * param
+        exp_avg.lerp_(g, 1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (exp_avg_sq.sqrt() / state[2]).add_(eps)
+        param.addcdiv_(exp_avg, denom, value=-float(state[1]))
 
     def loss_finalize(self, part, c, terms, alpha, gamma, alpha_f, loss, lcoef):
         """terms bitmask: 1 dice, 2 ce/bce, 4 focal.  lcoef (fp32):
@@ -336,6 +412,8 @@ class EmuBackend:
             lcoef[2 * c] = (1.0 / V).float() if terms & 2 else 0.0
             lcoef[2 * c + 1] = (1.0 / V).float() if terms & 4 else 0.0
             lcoef[2 * c + 2] = float(gamma)
+            if pt[3 * c + 3] > 0:
+                val = val * float("nan")
         loss.copy_(val.float())
 
     def loss_bwd(self, logits, labels, lcoef, gscale, dlogits):

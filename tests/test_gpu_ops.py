@@ -270,12 +270,22 @@ def test_head_and_losses(be, c):
     alpha = torch.linspace(0.5, 1.5, c)
     for terms in (1, 2, 4, 3, 5, 7):
         for gamma in (2.0, 3.0):
-            npart = 6 if c == 1 else 3 * c + 3
+            npart = be.part_size(c)
             part_e = torch.zeros(npart, dtype=torch.float64)
-            EMU.loss_partials(z, t, gamma, 0.25, part_e)
+            met_e = torch.zeros(z.shape[0], c, 3, dtype=torch.float64)
+            EMU.loss_partials(z, t, gamma, 0.25, part_e, met_e)
             part_c = torch.zeros(npart, dtype=torch.float64, device="cuda")
-            be.loss_partials(z.cuda(), t.cuda(), gamma, 0.25, part_c)
+            met_c = torch.zeros(z.shape[0], c, 3, dtype=torch.float64, device="cuda")
+            be.loss_partials(z.cuda(), t.cuda(), gamma, 0.25, part_c, met_c)
             assert rel(part_c, part_e) < 2e-6
+            assert torch.equal(met_c.cpu(), met_e)          # counts: exact
+            out_e, out_c = torch.empty(2), torch.empty(2, device="cuda")
+            EMU.metric_finalize(met_e, out_e)
+            be.metric_finalize(met_c, out_c)
+            assert (out_c.cpu() - out_e).abs().max() < 1e-6
+            met_p = torch.zeros_like(met_c)                 # the same sums from materialised probabilities
+            be.metric_partials(p_c, t.cuda(), 0.5, met_p)
+            assert torch.equal(met_p.cpu(), met_e)
             nl = 5 if c == 1 else 2 * c + 3
             loss_e, lc_e = torch.empty(()), torch.empty(nl)
             EMU.loss_finalize(part_e, c, terms, alpha, gamma, 0.25, loss_e, lc_e)
