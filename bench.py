@@ -10,12 +10,19 @@ N > 1 is launched by the driver as ``python -m torch.distributed.run --nproc-per
 tensors; no optimizer -- the metric is "fwd+bwd") over one synthetic batch.
 
 Timing: CUDA events on the launching stream, one event pair per step, L2 flushed (256 MiB write)
-before every timed step outside the event pair, max over ranks; W >= 3 warm-up steps.
-  value : inputs resident in HBM, CUDA-graph replay of the step captured through the public API.
+before every timed step outside the event pair, max over ranks; W >= 3 warm-up steps.  The clock sampler
+(nvidia-smi) runs on EVERY rank and is started before the warm-up, i.e. well before the barrier that aligns the
+timed region (round 1 started it on rank 0 between the barrier and the first step: the other ranks waited in
+their first all-reduce and the N=8 line was wrong).
+  value : inputs resident in HBM, CUDA-graph replay of the step (GraphedStep); mean of the K timed steps
+          (median / min / max reported beside it; sum of the event times is checked against the wall clock).
   e2e   : same, but every step copies x (fp32) and labels (int64) from pinned host memory and reads
           the loss back to the host inside the timed region.
-  roofline     : the dominant kernel of the step (per-kernel CUDA-event timing of one eager step),
-                 algorithmic bytes/flops / its mean duration vs MEASURED_PEAKS.json.
+  roofline     : the kernel with the largest share of the step, from ONE serialised, instrumented eager step
+                 (weight gradients on the main stream, device synchronised between ops, so an event pair times a
+                 kernel and not a queue): algorithmic bytes/flops / its mean duration vs
+                 MEASURED_PEAKS.json; per network block (10 VNet3d blocks) in `roofline_blocks`.
+  variants (N=1 only): forward-only, optimizer-inclusive (fused AdamW inside the graph) and the fp32 parity mode.
   cpu_baseline : the CPU oracle (oracle/, a restatement of the reference's PyTorch path: "port")
                  timed on this box's host cores, same shapes/seeds, fwd+loss+bwd, rank 0, N=1.
 """
@@ -189,12 +196,12 @@ def _emit(line: dict):
 # ------------------------------------------------------------------------------------------------
 class TimedBackend:
     TIMED = ("conv", "wgrad", "apply", "gn_bwd_reduce", "gn_bwd_apply", "gn_finalize", "gn_bwd_finalize",
-             "apply_gn", "gn_bwd_reduce_gn", "gn_bwd_apply_gn", "pack_weight", "unpack_wgrad", "colsum",
-             "head_probs", "head_fwd", "head_bwd", "loss_partials", "loss_finalize", "loss_bwd", "pool_fwd",
-             "pool_bwd")       # (pack_many / unpack_many build their descriptor tables on the host: not event-timed here)
+             "apply_gn", "gn_bwd_reduce_gn", "gn_bwd_apply_gn", "gn_bwd_fused_gn", "pack_weight", "unpack_wgrad",
+             "colsum", "head_probs", "head_fwd", "head_bwd", "loss_partials", "loss_finalize", "loss_bwd", "pool_fwd",
+             "pool_bwd", "pack_many", "unpack_many", "dropout_masks", "metric_finalize", "adam_step")
 
     def __init__(self, inner):
-        self.inner, self.records = inner, []
+        self.inner, self.records, self.tag = inner, [], "other"
 
     def __getattr__(self, name):
         fn = getattr(self.inner, name)
@@ -202,11 +209,15 @@ class TimedBackend:
             return fn
 
         def wrapped(*a, **k):
+            # serialised: nothing else is in flight when the op starts, and it has finished before the next one is
+            # issued -- the event pair brackets this op's kernel(s) only (plus ~2 us of event overhead)
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            self.records.append((name, self._describe(name, a), e0, e1, self._work(name, a)))
+            torch.cuda.synchronize()
+            self.records.append((name, self._describe(name, a), e0, e1, self._work(name, a), self.tag))
             return r
         return wrapped
 
@@ -224,6 +235,8 @@ class TimedBackend:
         if name == "wgrad":
             kind, dims, x, dy = a[:4]
             return f"wgrad[k{kind}] {x.shape[-1]}x{dy.shape[-1]}@{tuple(dy.shape[1:4])}"
+        if name == "gn_bwd_fused_gn":
+            name = "gn_bwd_fused(reduce+barrier+apply)"
         t = next((v for v in a if isinstance(v, torch.Tensor) and v.dim() == 5), None)
         return f"{name} {t.shape[-1]}@{tuple(t.shape[1:4])}" if t is not None else name
 
@@ -251,13 +264,16 @@ class TimedBackend:
 
     def summary(self):
         torch.cuda.synchronize()
-        agg = {}
-        for name, desc, e0, e1, (by, fl) in self.records:
+        agg, blocks = {}, {}
+        for name, desc, e0, e1, (by, fl), tag in self.records:
             ms = e0.elapsed_time(e1)
             d = agg.setdefault(desc, {"ms": 0.0, "n": 0, "bytes": by, "flops": fl})
             d["ms"] += ms
             d["n"] += 1
-        return agg
+            b = blocks.setdefault(tag, {"ms": 0.0, "n": 0})
+            b["ms"] += ms
+            b["n"] += 1
+        return agg, blocks
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,15 +363,23 @@ def cpu_baseline_sample():
                       f"{cores} host threads; median {t * 1e3:.0f} ms/step"}
 
 
+# per-block algorithmic work of VNet3d(1,2) 96^3 B=2 bf16, fwd+bwd: (GFLOP, MB)
+VNET96_BLOCKS = {"in_tr": (3.17, 353.9), "down_tr32": (78.8, 481.8), "down_tr64": (57.8, 147.9),
+                 "down_tr128": (28.9, 47.4), "down_tr256": (14.4, 53.6), "up_tr256": (28.9, 45.7),
+                 "up_tr128": (57.8, 134.2), "up_tr64": (78.8, 425.3), "up_tr32": (84.3, 1302.4),
+                 "out_tr": (0.34, 247.7)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the fwd-only / optimizer / fp32 variants (N=1)")
     ap.add_argument("--workload", default="vnet3d96", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     _capture_stdout()
@@ -378,6 +402,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the b200 arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    sampler.start()                   # every rank, long before the barrier-aligned timed region
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
@@ -385,49 +411,74 @@ def main():
         b200.enable_data_parallel()
     b200.set_precision(args.precision)
 
-    torch.manual_seed(0)
-    model = {"vnet3d": b200.VNet3d, "unet3d": b200.UNet3d, "unet2d": b200.UNet2d}[ARCH](1, NUMCLASS)
-    model.apply(b200.initialize_weights)
-    model = model.to(dev).train()
+    def make_model():
+        torch.manual_seed(0)
+        m = {"vnet3d": b200.VNet3d, "unet3d": b200.UNet3d, "unet2d": b200.UNet2d}[ARCH](1, NUMCLASS)
+        m.apply(b200.initialize_weights)
+        return m.to(dev).train()
+
+    model = make_model()
     losscls = getattr(b200, LOSS)
     lossfn = losscls(torch.ones(NUMCLASS, device=dev)) if LOSS.startswith("Mutil") else losscls()
     xh, yh = make_batch(rank, world)
     xh, yh = xh.pin_memory(), yh.pin_memory()
     x, y = xh.to(dev), yh.to(dev)
-    torch.manual_seed(100 + rank)
+    # the SAME seed on every rank: a rank takes its rows of the global-batch dropout draw
+    torch.manual_seed(100)
     be = runtime.cuda_backend()
 
-    def eager_step(xx, yy):
-        for p in model.parameters():
+    def eager_step(xx, yy, mdl=None):
+        mdl = mdl or model
+        for p in mdl.parameters():
             p.grad = None
-        logits, _ = model(xx)
+        logits, _ = mdl(xx)
         loss = lossfn(logits, yy)
         loss.backward()
         return loss
-
-    # ---- launches per step + per-kernel timing (one eager, instrumented step)
-    eager_step(x, y)
-    torch.cuda.synchronize()
-    c0 = be.launch_count
-    tb = TimedBackend(be)
-    runtime._set_backend_for_testing(tb)
-    eager_step(x, y)
-    runtime._set_backend_for_testing(None)
-    launches = be.launch_count - c0
-    kern = tb.summary()
 
     use_graph = not args.no_graph
     graphed = None
     if use_graph:
         try:
-            # data parallel: GraphedStep keeps the NCCL collectives outside its two graphs (split mode), so a
-            # rank that has to fall back to eager launches still issues the same collectives in the same order
-            graphed = GraphedStep(model, lossfn, x, y, warmup=1)
+            graphed = GraphedStep(model, lossfn, x, y, warmup=2)
         except Exception as e:  # pragma: no cover
             print(f"[bench] rank {rank}: CUDA graph capture failed ({type(e).__name__}: {e}); eager launches",
                   file=sys.stderr)
             graphed = GraphedStep(model, lossfn, x, y, warmup=1, use_graph=False)
             torch.cuda.synchronize()
+    n_graphs = len(graphed.graphs) if graphed is not None else 0
+
+    # ---- launches per step (counted on the step as it is benchmarked: one eager GraphedStep pass)
+    torch.cuda.synchronize()
+    c0 = be.launch_count
+    if graphed is not None:
+        graphed._eager_step()
+    else:
+        eager_step(x, y)
+    torch.cuda.synchronize()
+    launches = be.launch_count - c0
+
+    # ---- per-kernel / per-block timing: ONE serialised, instrumented eager step (rank 0 only; no collectives)
+    kern, blocks = {}, {}
+    if rank == 0:
+        dp_prev = runtime.dp_state()
+        runtime.disable_data_parallel()
+        os.environ["B200SEG_WGRAD_SIDE_STREAM"] = "0"
+        os.environ["B200SEG_CHECK_LABELS"] = "0"
+        tb = TimedBackend(be)
+        runtime._set_backend_for_testing(tb)
+        try:
+            probe = GraphedStep(model, lossfn, x, y, warmup=1, use_graph=False)
+            tb.records.clear()
+            probe._eager_step()
+            kern, blocks = tb.summary()
+        finally:
+            runtime._set_backend_for_testing(None)
+            del os.environ["B200SEG_WGRAD_SIDE_STREAM"]
+            del os.environ["B200SEG_CHECK_LABELS"]
+            if dp_prev[0]:
+                runtime.enable_data_parallel(dp_prev[1])
+        del probe
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -454,8 +505,6 @@ def main():
             graphed()                      # replays on the static (HBM-resident) input buffers
         else:
             eager_step(x, y)
-
-    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
     host_losses = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_values = []
@@ -494,31 +543,71 @@ def main():
     for _ in range(args.warmup):
         resident_step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     ms = timed(resident_step, args.steps)
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if sum(ms) * 1e-3 > wall * 1.02 + 1e-3:
+        raise SystemExit(f"[bench] rank {rank}: inconsistent timing: event sum {sum(ms):.2f} ms > wall {wall * 1e3:.2f} ms")
     e2e_loop(2)
     barrier()
-    ms_e2e = [e2e_loop(args.steps)] * args.steps
+    ms_e2e = e2e_loop(args.steps)
     barrier()
 
-    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sum(ms), ms_e2e * args.steps, statistics.median(ms), min(ms), max(ms)], dtype=torch.float64,
+                       device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     t_step = tot[0].item() / args.steps * 1e-3
     t_e2e = tot[1].item() / args.steps * 1e-3
     vox_step = world * BATCH_PER_GPU * voxels_per_sample()
 
+    # ---- variants (single GPU): forward only, optimizer inclusive, fp32 parity mode
+    variants = {}
+    if world == 1 and use_graph and not args.no_variants:
+        vox1 = BATCH_PER_GPU * voxels_per_sample()
+
+        def time_fn(fn, k, w=3):
+            for _ in range(w):
+                fn()
+            return statistics.median(timed(fn, k))
+        try:
+            # forward only (train mode, masks drawn): one graph around model(x) under no_grad
+            gfw = torch.cuda.CUDAGraph()
+            with torch.no_grad():
+                model(x)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(gfw):
+                    model(x)
+            t_fwd = time_fn(gfw.replay, 20)
+            variants["fwd_only"] = {"ms_per_step": t_fwd, "voxels_per_s": vox1 / (t_fwd * 1e-3)}
+            del gfw
+            # optimizer inclusive: fused AdamW (one launch on the flat buckets) inside the step graph
+            m2 = make_model()
+            opt = b200.FusedAdamW(m2.parameters(), lr=1e-3)
+            g2 = GraphedStep(m2, lossfn, x, y, warmup=2, optimizer=opt)
+            t_opt = time_fn(g2, 20)
+            variants["with_fused_adamw"] = {"ms_per_step": t_opt, "voxels_per_s": vox1 / (t_opt * 1e-3)}
+            del g2, opt, m2
+            # fp32 parity mode (the kernel set that meets north_star's 1e-3 / identical-argmax bar)
+            if args.precision == "bf16":
+                b200.set_precision("fp32")
+                m3 = make_model()
+                g3 = GraphedStep(m3, lossfn, x, y, warmup=1)
+                t32 = time_fn(g3, 5, w=1)
+                variants["fp32_parity_mode"] = {"ms_per_step": t32, "voxels_per_s": vox1 / (t32 * 1e-3)}
+                del g3, m3
+                b200.set_precision("bf16")
+        except Exception as e:  # pragma: no cover
+            variants["error"] = f"{type(e).__name__}: {e}"
+            b200.set_precision(args.precision)
+
     if rank == 0:
         peaks = load_peaks()
-        # dominant kernel of the step
-        top = max(kern.items(), key=lambda kv: kv[1]["ms"])
-        desc, d = top
+        total_ms = max(1e-9, sum(v["ms"] for v in kern.values()))
+        # dominant kernel of the step = largest share of the serialised step time
+        desc, d = max(kern.items(), key=lambda kv: kv[1]["ms"])
         dur = d["ms"] / d["n"] * 1e-3
         gbs = d["bytes"] / dur / 1e9
         tfs = d["flops"] / dur / 1e12
@@ -533,42 +622,68 @@ def main():
         try:                          # kernel/shape was captured (profiles/ncu_traffic.json)
             with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
                 traffic = json.load(f).get(desc, {}).get("dram_bytes")
-        except OSError:
+        except (OSError, ValueError):
             pass
         roof.update({"kernel": desc, "launches_per_step": d["n"], "avg_us": dur * 1e6, "traffic": traffic,
-                     "peaks": peaks["source"],
-                     "share_of_step": d["ms"] / max(1e-9, sum(v["ms"] for v in kern.values()))})
+                     "algorithmic_bytes": d["bytes"], "algorithmic_flops": d["flops"],
+                     "peaks": peaks["source"], "share_of_step": d["ms"] / total_ms,
+                     "how": "serialised eager step: weight gradients on the main stream, device sync between ops"})
         ranked_all = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])
-        ranked = ranked_all[:12]
+        ranked = ranked_all[:14]
         if os.environ.get("B200SEG_BENCH_TABLE"):        # development aid: the full per-op table of the eager pass
             with open(os.environ["B200SEG_BENCH_TABLE"], "w") as f:
                 for k, v in ranked_all:
                     f.write(f"{v['ms'] * 1e3:9.1f} us  x{v['n']:3d}  {k}\n")
+                for k, v in sorted(blocks.items(), key=lambda kv: -kv[1]["ms"]):
+                    f.write(f"block {k:12s} {v['ms'] * 1e3:9.1f} us  x{v['n']:3d}\n")
+        block_table = None
+        if args.workload == "vnet3d96":
+            block_table = {}
+            for bname, (gf, mb) in VNET96_BLOCKS.items():
+                mb_ = mb * (1.0 if args.precision == "bf16" else 2.0)     # fp32 storage doubles the activation bytes
+                t_tc = gf / 1e3 / peaks["bf16_tflops_burst"]
+                t_hbm = mb_ / 1e3 / peaks["hbm_gbs"]
+                t_roof = max(t_tc, t_hbm)
+                t_meas = blocks.get(bname, {}).get("ms", 0.0) * 1e-3
+                block_table[bname] = {"bound": "tensor" if t_tc > t_hbm else "hbm", "roof_us": t_roof * 1e6,
+                                      "measured_us": t_meas * 1e6, "launches": blocks.get(bname, {}).get("n", 0),
+                                      "frac": (t_roof / t_meas) if t_meas > 0 else None}
+            block_table["other(pack/unpack/masks)"] = {"measured_us": blocks.get("other", {}).get("ms", 0.0) * 1e3,
+                                                       "launches": blocks.get("other", {}).get("n", 0)}
         step_roof = {"hbm_GBps": STEP_MB / 1e3 / t_step, "tflops": STEP_GFLOP / 1e3 / t_step,
                      "frac_hbm": STEP_MB / 1e3 / t_step / peaks["hbm_gbs"],
                      "frac_tensor": STEP_GFLOP / 1e3 / t_step / peaks["bf16_tflops"],
-                     "algorithmic_GFLOP": STEP_GFLOP, "algorithmic_MB": STEP_MB}
+                     "algorithmic_GFLOP": STEP_GFLOP, "algorithmic_MB": STEP_MB,
+                     "serialised_kernel_sum_ms": total_ms}
         line = {
             "metric": "voxels_per_sec_fwd_bwd", "value": vox_step / t_step, "unit": "voxels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
+            "ms_per_step_median": tot[2].item(), "ms_per_step_min": tot[3].item(), "ms_per_step_max": tot[4].item(),
             "config": {"workload": WL_DESC + ", fwd (train mode, dropout masks drawn) + " + LOSS +
-                                   " + bwd of all parameter tensors"
-                                   + (" + NCCL SUM all-reduce of the flat fp32 gradient bucket" if world > 1 else ""),
+                                   " (+ per-step Dice accuracy from the same pass) + bwd of all parameter tensors"
+                                   + (" + NCCL SUM all-reduce of the flat fp32 gradient bucket (two pieces, the first "
+                                      "overlapping the rest of backward)" if world > 1 else ""),
                        "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
                        "l2": "value: 256 MiB flush before every timed step; e2e: one timed region over all steps, "
                              "no flush (inputs arrive from the host every step; per-step working set > 1 GB >> 126 MB L2)",
                        "e2e_pipeline": "H2D of step i+1 on a copy stream overlaps step i; the loss of every step is "
                                        "copied back and read on the host while the next step runs (one step of lag)",
-                       "cuda_graph": bool(use_graph and (graphed.graph is not None or graphed.graph_a is not None)),
+                       "cuda_graph": bool(use_graph and n_graphs > 0), "graphs_per_step": n_graphs,
+                       "nccl_inside_graph": bool(world > 1 and n_graphs == 1),
                        "precision_mode": args.precision},
             "e2e": {"value": vox_step / t_e2e, "unit": "voxels/s", "ms_per_step": t_e2e * 1e3,
                     "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "clocks": clocks, "roofline": roof, "roofline_step": step_roof,
-            "top_kernels": [{"kernel": k, "ms_per_step": v["ms"], "launches": v["n"]} for k, v in ranked],
-            "wall_s_timed_region": wall,
+            "clocks": clocks, "roofline": roof, "roofline_step": step_roof, "roofline_blocks": block_table,
+            "variants": variants,
+            "top_kernels": [{"kernel": k, "ms_per_step": v["ms"], "launches": v["n"],
+                             "GBps": v["bytes"] / (v["ms"] / v["n"] * 1e-3) / 1e9 if v["ms"] > 0 else None,
+                             "TFLOPs": v["flops"] / (v["ms"] / v["n"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
+                            for k, v in ranked],
+            "wall_s_timed_region": wall, "event_sum_s_timed_region": sum(ms) * 1e-3,
+            "final_loss": loss_values[-1] if loss_values else None,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()

@@ -151,6 +151,7 @@ class Engine:
         """ONE launch packs every conv operand of the step (forward and data-gradient layouts).
         specs: [(wname, kind, vox_out, vox_in, needs_dgrad)]."""
         reqs, keys = [], []
+        self._tag(None)
         for wname, kind, vox_out, vox_in, dgrad in specs:
             reqs.append((self.P[wname], kind, "fwd", self.T, self.dims, vox_out))
             keys.append((wname, "fwd"))
@@ -178,9 +179,16 @@ class Engine:
 
     def _finish_backward(self) -> None:
         self._join_side()
+        self._tag(None)
         self.be.unpack_many(self._unpack_list)
         self._unpack_list = []
         self._packs = {}
+
+    def _tag(self, wname: Optional[str]) -> None:
+        """instrumentation hook: a profiling wrapper around the backend (bench.py) learns which network block
+        (``in_tr``, ``down_tr32`` ... -- the first component of the parameter name) the next launches belong to"""
+        if hasattr(self.be, "tag"):
+            self.be.tag = wname.split(".")[0] if wname else "other"
 
     # ---------------------------------------------------------------- forward primitives
     def conv_raw(self, kind: int, wname: str, bname: Optional[str], x: Tensor, y: Tensor,
@@ -196,6 +204,7 @@ class Engine:
                 out_sp: Sequence[int], cout: int) -> Layer:
         """conv + stats + finalize.  The activation itself is produced later by ``apply``."""
         L = Layer(kind, wname, bname, gname, x=x)
+        self._tag(wname)
         n = x.shape[0]
         L.y = self.new(x, out_sp, cout)
         stats = self.zeros((n, cout, 2), torch.float64, x.device)
@@ -219,6 +228,7 @@ class Engine:
     def head(self, wname: str, bname: str, x: Tensor, sp0, ncls: int) -> Tuple[Layer, Tensor, Optional[Tensor]]:
         """OutputTransition3d / UNet head: 1x1 conv to the classes + sigmoid/softmax (VNet3d.py:90-99).
         Inference form (``mask_threshold`` set; predict, model/modelVNet.py:655-676): the uint8 mask directly."""
+        self._tag(wname)
         if self.mask_threshold is not None:
             mask = torch.empty((x.shape[0],) + tuple(sp0), dtype=torch.uint8, device=x.device)
             if not self.be.head_mask(x, self.P[wname], self.P[bname], mask, float(self.mask_threshold)):
@@ -236,12 +246,14 @@ class Engine:
         return Lh, logits, probs
 
     def head_backward(self, Lh: Layer, g_logits: Tensor) -> Tensor:
+        self._tag(Lh.wname)
         dx = torch.empty(Lh.x.shape, dtype=self.T, device=g_logits.device)
         if self.be.head_bwd(Lh.x, g_logits, self.P[Lh.wname], dx, self._grad_view(Lh.wname), self._grad_view(Lh.bname)):
             return dx
         return self.bwd_layer(Lh, g_logits, True, dx_out=dx)
 
     def act(self, L: Layer, out: Tensor, L2: Optional[Layer] = None, res: Optional[Tensor] = None) -> Tensor:
+        self._tag(L.wname)
         if L.gn is not None:
             self.be.apply_gn(L.y, L.gn, L2.y if L2 is not None else None, L2.gn if L2 is not None else None, res, out)
         else:
@@ -258,6 +270,7 @@ class Engine:
         the layer's activation output (or w.r.t. the raw conv output when the layer has no
         GroupNorm).  Returns the gradient w.r.t. the layer input (written to ``dx_out``)."""
         be = self.be
+        self._tag(L.wname)
         n, cout = L.y.shape[0], L.y.shape[-1]
         dev = L.y.device
         vox = L.y.numel() // (n * cout)

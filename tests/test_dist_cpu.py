@@ -50,7 +50,23 @@ def _worker(rank, world, port, arch, q):
     loss.backward()
     b200.disable_data_parallel()
     err = max(((p.grad - ref[n]).norm() / (ref[n].norm() + 1e-12)).item() for n, p in model.named_parameters())
-    q.put((rank, abs(loss.item() - loss_g.item()), err))
+    # train mode: every rank takes ITS rows of the global-batch dropout draw (same seed on all ranks), and
+    # GraphedStep (engine-driven, bucketed all-reduce) must agree with the autograd path on the global batch
+    from pytorchdeeplearing_b200.graphed import GraphedStep
+    model.train()
+    for p in model.parameters():
+        p.grad = None
+    torch.manual_seed(21)
+    logits, _ = model(x)
+    loss_t = lossfn(logits, y)
+    loss_t.backward()
+    ref_t = {n: p.grad.clone() for n, p in model.named_parameters()}
+    b200.enable_data_parallel()
+    torch.manual_seed(21)
+    step = GraphedStep(model, lossfn, x[sl], y[sl], warmup=1, use_graph=False)
+    b200.disable_data_parallel()
+    err_t = max(((p.grad - ref_t[n]).norm() / (ref_t[n].norm() + 1e-12)).item() for n, p in model.named_parameters())
+    q.put((rank, max(abs(loss.item() - loss_g.item()), abs(step.loss.item() - loss_t.item())), max(err, err_t)))
     dist.destroy_process_group()
 
 

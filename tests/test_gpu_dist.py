@@ -44,7 +44,30 @@ def _worker(rank, world, port, q):
     loss.backward()
     torch.cuda.synchronize()
     errs = sorted(((p.grad - ref[n]).norm() / (ref[n].norm() + 1e-12)).item() for n, p in model.named_parameters())
-    q.put((rank, abs(loss.item() - loss_g.item()), errs[len(errs) // 2], errs[-1]))
+    b200.disable_data_parallel()
+    # train mode through GraphedStep (captured, NCCL inside the graph when the stack allows it): every rank takes ITS
+    # rows of the global-batch dropout draw (same seed everywhere), so the sharded step equals the single-GPU step on
+    # the global batch -- loss and all-reduced gradients
+    from pytorchdeeplearing_b200.graphed import GraphedStep
+    model.train()
+    for p in model.parameters():
+        p.grad = None
+    torch.manual_seed(31)
+    logits, _ = model(x)
+    loss_t = lossfn(logits, y)
+    loss_t.backward()
+    ref_t = {n: p.grad.clone() for n, p in model.named_parameters()}
+    b200.enable_data_parallel()
+    step = GraphedStep(model, lossfn, x[sl], y[sl], warmup=1)
+    torch.manual_seed(31)
+    loss_s = step(x[sl], y[sl])
+    torch.cuda.synchronize()
+    errs_t = sorted(((p.grad - ref_t[n]).norm() / (ref_t[n].norm() + 1e-12)).item()
+                    for n, p in model.named_parameters())
+    ngraphs = len(step.graphs)
+    b200.disable_data_parallel()
+    q.put((rank, max(abs(loss.item() - loss_g.item()), abs(loss_s.item() - loss_t.item())),
+           max(errs[len(errs) // 2], errs_t[len(errs_t) // 2]), max(errs[-1], errs_t[-1]), ngraphs))
     dist.destroy_process_group()
 
 
@@ -60,6 +83,7 @@ def test_nccl_two_rank_matches_global_batch():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, dloss, med, worst in res:
+    for rank, dloss, med, worst, ngraphs in res:
         assert dloss < 1e-5, (rank, dloss)
         assert med < 5e-3 and worst < 5e-2, (rank, med, worst)
+        print(f"rank {rank}: graphs per step = {ngraphs} (1 = NCCL captured inside the step graph)")
