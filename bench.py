@@ -210,8 +210,11 @@ class TimedBackend:
 
         def wrapped(*a, **k):
             # serialised: nothing else is in flight when the op starts, and it has finished before the next one is
-            # issued -- the event pair brackets this op's kernel(s) only (plus ~2 us of event overhead)
+            # issued.  A ~1 ms spin kernel is queued first so that the start event, the op's kernel(s) and the stop
+            # event are all enqueued while the GPU is still busy: the event pair then brackets device execution only,
+            # not the host's launch path (ctypes call, descriptor tables), which a CUDA-graph replay does not pay
             torch.cuda.synchronize()
+            torch.cuda._sleep(2_000_000)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = fn(*a, **k)

@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/b200seg.h"
 
@@ -137,6 +141,45 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A step is a chain of ~150 short kernels; every kernel starts with
+// ``griddepcontrol.wait`` (all memory of the kernels before it in the stream is visible after it) followed by
+// ``griddepcontrol.launch_dependents``, and every launch carries the programmatic-stream-serialization attribute:
+// the next kernel of the chain is launched and its CTAs are scheduled while the last wave of this one is still
+// running, so the launch latency (~2-3 us per boundary inside a CUDA graph) leaves the critical path.  Because the
+// wait is the first instruction, every kernel still sees the complete output of ALL its predecessors (the chain is
+// transitive).  B200SEG_PDL=0 turns the attribute off (the device instructions are then no-ops).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#define PDL_ENTER() b200seg::pdl_enter()
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200SEG_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);     // errors surface in B200_LAUNCH_CHECK
 }
 
 inline int num_sms(int dev) {

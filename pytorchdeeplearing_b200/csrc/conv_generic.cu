@@ -36,6 +36,7 @@ struct ConvArgs {
 
 template <typename TX, typename TW, typename TY, int BN>
 __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs<TX, TW, TY> a) {
+  PDL_ENTER();
   constexpr int BM = 4096 / BN;
   constexpr int BK = 16;
   constexpr int PASSES = BM / 64;
@@ -271,13 +272,13 @@ static int launch_conv(const ConvArgs<TX, TW, TY>& a, int nbatch, cudaStream_t s
   dim3 block(256);
   if (a.Ncols <= 16) {
     dim3 grid((a.Mrows + 255) / 256, 1, nbatch);
-    conv_ffma_kernel<TX, TW, TY, 16><<<grid, block, 0, st>>>(a);
+    launch_k(conv_ffma_kernel<TX, TW, TY, 16>, grid, block, 0, st, a);
   } else if (a.Ncols <= 32) {
     dim3 grid((a.Mrows + 127) / 128, 1, nbatch);
-    conv_ffma_kernel<TX, TW, TY, 32><<<grid, block, 0, st>>>(a);
+    launch_k(conv_ffma_kernel<TX, TW, TY, 32>, grid, block, 0, st, a);
   } else {
     dim3 grid((a.Mrows + 63) / 64, (a.Ncols + 63) / 64, nbatch);
-    conv_ffma_kernel<TX, TW, TY, 64><<<grid, block, 0, st>>>(a);
+    launch_k(conv_ffma_kernel<TX, TW, TY, 64>, grid, block, 0, st, a);
   }
   B200_LAUNCH_CHECK();
   return B200SEG_OK;

@@ -57,6 +57,7 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t 
 
 template <int CIN, int COUT, int KD>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloArgs p) {
+  PDL_ENTER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   constexpr int CP = CIN / 8;                                // 8-channel planes
@@ -468,7 +469,7 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.cp_async = cpa;
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = sms < p.nitems ? sms : p.nitems;
-#define HALO_LAUNCH(CI, CO, K) conv_halo_kernel<CI, CO, K><<<grid, kHaloThreads, smem_bytes, st>>>(p)
+#define HALO_LAUNCH(CI, CO, K) launch_k(conv_halo_kernel<CI, CO, K>, grid, kHaloThreads, smem_bytes, st, p)
   if (p.kd == 3) {
     if (p.Cin == 16 && p.Cout == 16) HALO_LAUNCH(16, 16, 3);
     else if (p.Cin == 16) HALO_LAUNCH(16, 32, 3);

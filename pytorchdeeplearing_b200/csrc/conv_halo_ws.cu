@@ -61,6 +61,7 @@ __device__ __forceinline__ uint64_t ws_nosw_desc(uint32_t lbo_bytes, uint32_t sb
 
 template <int CIN, int NT, int NACC>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWsArgs p) {
+  PDL_ENTER();
   constexpr int CP = CIN / 8;                                // 8-channel planes
   constexpr uint32_t PLANE = WS_PH * WS_PW * 16u;            // bytes of one plane of one slice
   constexpr uint32_t SLICE = (uint32_t)CP * PLANE;
@@ -428,7 +429,7 @@ static int conv_halows_launch(HaloWsArgs& p, int device, int maxsm, cudaStream_t
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   const int sms = num_sms(device);
   const int grid = sms < p.nitems ? sms : p.nitems;
-  conv_halows_kernel<CIN, NT, NACC><<<grid, kWsThreads, smem_bytes, st>>>(p);
+  launch_k(conv_halows_kernel<CIN, NT, NACC>, grid, kWsThreads, smem_bytes, st, p);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

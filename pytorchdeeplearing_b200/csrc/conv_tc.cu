@@ -101,6 +101,7 @@ __device__ __forceinline__ int stat_col(int lane) {
 template <int BKC, int NCH>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+  PDL_ENTER();
   constexpr uint32_t SWZ = BKC * 2;                 // bytes per smem row = swizzle span
   constexpr uint32_t A_BYTES = 128u * SWZ;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -528,9 +529,9 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const int nch = regstats_off ? 0 : (p.Cout == 16 ? 1 : (p.Cout == 32 ? 2 : 0));
 #define TC_LAUNCH(B)                                                                         \
   do {                                                                                       \
-    if (nch == 1) conv_tc_kernel<B, 1><<<grid, kTcThreads, smem_bytes, st>>>(tmA, tmB, p);          \
-    else if (nch == 2) conv_tc_kernel<B, 2><<<grid, kTcThreads, smem_bytes, st>>>(tmA, tmB, p);     \
-    else conv_tc_kernel<B, 0><<<grid, kTcThreads, smem_bytes, st>>>(tmA, tmB, p);                   \
+    if (nch == 1) launch_k(conv_tc_kernel<B, 1>, grid, kTcThreads, smem_bytes, st, tmA, tmB, p);          \
+    else if (nch == 2) launch_k(conv_tc_kernel<B, 2>, grid, kTcThreads, smem_bytes, st, tmA, tmB, p);     \
+    else launch_k(conv_tc_kernel<B, 0>, grid, kTcThreads, smem_bytes, st, tmA, tmB, p);                   \
   } while (0)
   if (bkc == 64) TC_LAUNCH(64);
   else if (bkc == 32) TC_LAUNCH(32);

@@ -17,6 +17,7 @@ namespace b200seg {
 template <typename TO>
 __global__ void pack_weight_kernel(const float* __restrict__ w, TO* __restrict__ out, int T, int K, int N2, int N1,
                                    long long st, long long sk, long long sn2, long long sn1, int flip) {
+  PDL_ENTER();
   long long total = (long long)T * K * N2 * N1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -33,6 +34,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, TO* __restrict__
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int T, int K, int N,
                                     long long st, long long sk, long long sn) {
+  PDL_ENTER();
   // iterate in DESTINATION order when the destination's fastest index is t (st == 1): coalesced writes
   long long total = (long long)T * K * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -79,6 +81,7 @@ __device__ __forceinline__ int pack_find_desc(const PackDesc* __restrict__ table
 }
 
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  PDL_ENTER();
   __shared__ float s_tile[kPackMaxT][kPackCols + 1];
   __shared__ long long s_col[kPackCols];
   __shared__ int s_start[1024];
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackDesc* __restr
 
 // unpack: dst[t*st + k*sk + n*sn2] = src[(t*K + k)*N2 + n]   (N1 unused = 1)
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackDesc* __restrict__ table, int count) {
+  PDL_ENTER();
   __shared__ float s_tile[kPackMaxT][kPackCols + 1];
   __shared__ long long s_col[kPackCols];
   __shared__ int s_start[1024];
@@ -219,6 +223,7 @@ struct TableChunk {
   unsigned char b[3968];
 };
 __global__ void table_write_kernel(const __grid_constant__ TableChunk c, unsigned char* __restrict__ dst, int n) {
+  PDL_ENTER();
   for (int i = threadIdx.x * 16; i < n; i += blockDim.x * 16)
     *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(c.b + i);
 }
@@ -232,7 +237,7 @@ int ew_upload_table(const void* host, long long bytes, void* dev_dst, cudaStream
     const int n = (int)((bytes - off) < (long long)sizeof(TableChunk) ? (bytes - off) : (long long)sizeof(TableChunk));
     TableChunk c;
     memcpy(c.b, src + off, (size_t)n);
-    table_write_kernel<<<1, 256, 0, s>>>(c, dst + off, n);
+    launch_k(table_write_kernel, 1, 256, 0, s, c, dst + off, n);
   }
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -240,8 +245,8 @@ int ew_upload_table(const void* host, long long bytes, void* dev_dst, cudaStream
 
 int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack, cudaStream_t s) {
   if (count <= 0 || total_blocks <= 0) return B200SEG_OK;
-  if (unpack) unpack_multi_kernel<<<total_blocks, 256, 0, s>>>(static_cast<const PackDesc*>(table_dev), count);
-  else pack_multi_kernel<<<total_blocks, 256, 0, s>>>(static_cast<const PackDesc*>(table_dev), count);
+  if (unpack) launch_k(unpack_multi_kernel, total_blocks, 256, 0, s, static_cast<const PackDesc*>(table_dev), count);
+  else launch_k(pack_multi_kernel, total_blocks, 256, 0, s, static_cast<const PackDesc*>(table_dev), count);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -252,6 +257,7 @@ int ew_pack_multi(const void* table_dev, int count, int total_blocks, int unpack
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ scale, int C, int groups,
                                    double m, float eps, float* __restrict__ coef, float* __restrict__ mr) {
+  PDL_ENTER();
   const int n = blockIdx.x;
   const int cpg = C / groups;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -492,6 +498,7 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const T* __restrict__ y1,
                                                     const T* __restrict__ res, long long ldr, T* __restrict__ out,
                                                     long long ldo, int C, long long V, const GnRef gn1,
                                                     const GnRef gn2) {
+  PDL_ENTER();
   EW_PROLOGUE(C)
   float A1[VEC], B1[VEC], A2[VEC], B2[VEC];
   if (gn1.stats != nullptr) {
@@ -590,6 +597,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const T* __restri
                                                                const float* __restrict__ coef,
                                                                double* __restrict__ sums, int C, long long V,
                                                                const GnRef gn, const int staged) {
+  PDL_ENTER();
   EW_PROLOGUE(C)
   // dynamic smem: doubles [3][C] accumulators (unstaged path) | coefficient scratch; then floats: scratch [3][C],
   // A/B [2][C], staging [8 warps][3][C] (if staged)
@@ -702,6 +710,7 @@ __global__ void gn_bwd_finalize_kernel(const double* __restrict__ sums, const fl
                                        int groups, double vox, float* __restrict__ coef3,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ dbias) {
+  PDL_ENTER();
   const int cpg = C / groups;
   const double m = (double)cpg * vox;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
@@ -751,6 +760,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const T* __restric
                                                            const double* __restrict__ sums, int N,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ dbias) {
+  PDL_ENTER();
   EW_PROLOGUE(C)
   float A[VEC], B[VEC], P[VEC], Q[VEC], R[VEC];
   if (gn.stats != nullptr) {
@@ -850,6 +860,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const T* __restric
                                                               unsigned int* counter, int C, long long V,
                                                               const GnRef gn, int N, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ dbias) {
+  PDL_ENTER();
   EW_PROLOGUE(C)
   extern __shared__ double s_dyn[];
   double* s_d = s_dyn;                                                    // coefficient scratch (backward size)
@@ -970,6 +981,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const T* __restric
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
                                                      int C, long long V) {
+  PDL_ENTER();
   EW_PROLOGUE(C)
   extern __shared__ float s_red[];   // [C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_red[i] = 0.f;
@@ -996,6 +1008,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out,
                                                        long long ldo, int C, int OD, int OH, int OW, int kd) {
+  PDL_ENTER();
   const long long V = (long long)OD * OH * OW;
   EW_PROLOGUE(C)
   const int XH = OH * 2, XW = OW * 2, XD = OD * kd;
@@ -1028,6 +1041,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ x, 
                                                        const T* __restrict__ addend, long long lda,
                                                        T* __restrict__ gx, long long ldo, int C, int OD, int OH,
                                                        int OW, int kd) {
+  PDL_ENTER();
   const long long V = (long long)OD * OH * OW;
   EW_PROLOGUE(C)
   const int XH = OH * 2, XW = OW * 2, XD = OD * kd;
@@ -1085,6 +1099,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_probs_kernel(const float* __restrict__ z, float* __restrict__ p,
                                                          long long nvox, int C) {
+  PDL_ENTER();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
        i += (long long)gridDim.x * blockDim.x) {
     const float* zi = z + i * C;
@@ -1153,9 +1168,9 @@ int ew_pack_weight(const float* w, void* out, int out_dtype, int T, int K, int N
   if (blocks > 4096) blocks = 4096;
   if (blocks < 1) blocks = 1;
   if (out_dtype == B200SEG_BF16)
-    pack_weight_kernel<bf16><<<blocks, 256, 0, s>>>(w, static_cast<bf16*>(out), T, K, N2, N1, st, sk, sn2, sn1, flip);
+    launch_k(pack_weight_kernel<bf16>, blocks, 256, 0, s, w, static_cast<bf16*>(out), T, K, N2, N1, st, sk, sn2, sn1, flip);
   else
-    pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, static_cast<float*>(out), T, K, N2, N1, st, sk, sn2, sn1, flip);
+    launch_k(pack_weight_kernel<float>, blocks, 256, 0, s, w, static_cast<float*>(out), T, K, N2, N1, st, sk, sn2, sn1, flip);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -1166,7 +1181,7 @@ int ew_unpack_wgrad(const float* dwp, float* grad, int T, int K, int N, long lon
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   if (blocks < 1) blocks = 1;
-  unpack_wgrad_kernel<<<blocks, 256, 0, s>>>(dwp, grad, T, K, N, st, sk, sn);
+  launch_k(unpack_wgrad_kernel, blocks, 256, 0, s, dwp, grad, T, K, N, st, sk, sn);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -1175,7 +1190,7 @@ int ew_gn_finalize(const double* stats, const float* gamma, const float* beta, c
                    int groups, long long vox, float eps, float* coef, float* mr, cudaStream_t s) {
   B200_CHECK_ARG(C % groups == 0, "gn_finalize: C=%d not divisible by groups=%d", C, groups);
   double m = (double)(C / groups) * (double)vox;
-  gn_finalize_kernel<<<N, 256, 0, s>>>(stats, gamma, beta, scale, C, groups, m, eps, coef, mr);
+  launch_k(gn_finalize_kernel, N, 256, 0, s, stats, gamma, beta, scale, C, groups, m, eps, coef, mr);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -1207,8 +1222,7 @@ int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, co
     dim3 grid(ew_blocks(V, G, out->n, device, 3), out->n);
     const int mg = (g1 && g2 && g2->groups > g1->groups) ? g2->groups : (g1 ? g1->groups : 1);
     const size_t smem = gn_cta_doubles(C, mg, false) * sizeof(double) + (size_t)7 * C * sizeof(float);
-    apply_kernel<T, VEC><<<grid, 256, smem, s>>>(
-        static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
+    launch_k(apply_kernel<T, VEC>, grid, 256, smem, s, static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
         res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V,
         make_gnref(g1, C), make_gnref(g2, C));
   });
@@ -1230,8 +1244,7 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
     const size_t base = (3 * C + gn_cta_doubles(C, groups, false)) * sizeof(double) + (size_t)5 * C * sizeof(float);
     const size_t staged_bytes = base + (size_t)8 * 3 * C * sizeof(float);
     const int staged = (pow2g && G <= 32 && staged_bytes <= 46 * 1024) ? 1 : 0;
-    gn_bwd_reduce_kernel<T, VEC><<<grid, 256, staged ? staged_bytes : base, s>>>(
-        static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
+    launch_k(gn_bwd_reduce_kernel<T, VEC>, grid, 256, staged ? staged_bytes : base, s, static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
         make_gnref(gn, C), staged);
   });
   B200_LAUNCH_CHECK();
@@ -1243,7 +1256,7 @@ int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, 
                        cudaStream_t s) {
   B200_CHECK_ARG(C % groups == 0, "gn_bwd_finalize: C=%d not divisible by groups=%d", C, groups);
   int blocks = (C + 63) / 64;
-  gn_bwd_finalize_kernel<<<blocks, 64, 0, s>>>(sums, mr, gamma, scale, N, C, groups, (double)vox, coef3, dgamma,
+  launch_k(gn_bwd_finalize_kernel, blocks, 64, 0, s, sums, mr, gamma, scale, N, C, groups, (double)vox, coef3, dgamma,
                                                dbeta, dbias);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -1263,7 +1276,7 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
     dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
     const int groups = (gn && gn->stats) ? gn->groups : 1;
     const size_t smem = gn_cta_doubles(C, groups, true) * sizeof(double) + (size_t)8 * C * sizeof(float);
-    gn_bwd_apply_kernel<T, VEC><<<grid, 256, smem, s>>>(static_cast<const T*>(g->ptr), g->ld,
+    launch_k(gn_bwd_apply_kernel<T, VEC>, grid, 256, smem, s, static_cast<const T*>(g->ptr), g->ld,
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
                                                      static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
                                                      y->n, dgamma, dbeta, dbias);
@@ -1308,8 +1321,7 @@ int ew_gn_bwd_fused(const b200seg_tensor* g, const b200seg_tensor* y, const b200
     if ((256 % G) != 0) bx = (bx / G) * G;
     B200_CHECK_ARG(bx >= 1 && (long long)bx * y->n <= sms, "gn_bwd_fused: batch too large for a resident grid");
     dim3 grid(bx, y->n);
-    gn_bwd_fused_kernel<T, VEC><<<grid, 256, smem, s>>>(
-        static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, static_cast<T*>(dy->ptr), dy->ld,
+    launch_k(gn_bwd_fused_kernel<T, VEC>, grid, 256, smem, s, static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, static_cast<T*>(dy->ptr), dy->ld,
         sums, counter, C, V, make_gnref(gn, C), y->n, dgamma, dbeta, dbias);
   });
   B200_LAUNCH_CHECK();
@@ -1323,7 +1335,7 @@ int ew_colsum(const b200seg_tensor* dy, float* out, int device, cudaStream_t s) 
   EW_DISPATCH(dy, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, dy->n, device), dy->n);
-    colsum_kernel<T, VEC><<<grid, 256, C * sizeof(float), s>>>(static_cast<const T*>(dy->ptr), dy->ld, out, C, V);
+    launch_k(colsum_kernel<T, VEC>, grid, 256, C * sizeof(float), s, static_cast<const T*>(dy->ptr), dy->ld, out, C, V);
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -1340,7 +1352,7 @@ int ew_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, in
   EW_DISPATCH(out, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, out->n, device), out->n);
-    pool_fwd_kernel<T, VEC><<<grid, 256, 0, s>>>(static_cast<const T*>(x->ptr), x->ld, static_cast<T*>(out->ptr),
+    launch_k(pool_fwd_kernel<T, VEC>, grid, 256, 0, s, static_cast<const T*>(x->ptr), x->ld, static_cast<T*>(out->ptr),
                                                  out->ld, C, out->d, out->h, out->w, kd);
   });
   B200_LAUNCH_CHECK();
@@ -1361,8 +1373,7 @@ int ew_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* go, const b200seg
   EW_DISPATCH(gx, vok, {
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, go->n, device), go->n);
-    pool_bwd_kernel<T, VEC><<<grid, 256, 0, s>>>(
-        static_cast<const T*>(x->ptr), x->ld, static_cast<const T*>(go->ptr), go->ld,
+    launch_k(pool_bwd_kernel<T, VEC>, grid, 256, 0, s, static_cast<const T*>(x->ptr), x->ld, static_cast<const T*>(go->ptr), go->ld,
         addend ? static_cast<const T*>(addend->ptr) : nullptr, addend ? addend->ld : 0, static_cast<T*>(gx->ptr),
         gx->ld, C, go->d, go->h, go->w, kd);
   });
@@ -1375,7 +1386,7 @@ int ew_head_probs(const float* logits, float* probs, long long nvox_, int C, int
   long long cap = (long long)num_sms(device) * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  head_probs_kernel<<<(int)blocks, 256, 0, s>>>(logits, probs, nvox_, C);
+  launch_k(head_probs_kernel, (int)blocks, 256, 0, s, logits, probs, nvox_, C);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) loss_partials_binary_kernel(const float* 
                                                                    float gamma, float alpha_f,
                                                                    double* __restrict__ part,
                                                                    double* __restrict__ metric) {
+  PDL_ENTER();
   __shared__ double s_tmp[8];
   const long long base = (long long)blockIdx.y * vox;
   float aI = 0.f, aP = 0.f, aT = 0.f, aB = 0.f, aF = 0.f, mI = 0.f, mA = 0.f;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) loss_partials_multi_kernel(const float* _
                                                                   const long long* __restrict__ t, long long vox,
                                                                   float gamma, double* __restrict__ part,
                                                                   double* __restrict__ metric) {
+  PDL_ENTER();
   __shared__ double s_tmp[8];
   const long long base = (long long)blockIdx.y * vox;
   float aI[C], aP[C], aN[C], mI[C], mA[C];
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) loss_partials_multi_generic_kernel(const 
                                                                           long long vox, int C, float gamma,
                                                                           double* __restrict__ part,
                                                                           double* __restrict__ metric) {
+  PDL_ENTER();
   extern __shared__ float s_acc[];   // [3*C + 2] loss sums, [1] bad labels, [2*C] metric
   const int NS = 5 * C + 3;
   for (int i = threadIdx.x; i < NS; i += blockDim.x) s_acc[i] = 0.f;
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(256) loss_partials_multi_generic_kernel(const 
 // ---- per-step accuracy from the per-sample sums (model/metric.py:146-181): out[0] = dice_coeff (C == 1) or
 // multiclass_dice_coeff (mean over classes 1..C-1 of the per-sample-mean Dice), out[1] = the iou_coeff analogue
 __global__ void metric_finalize_kernel(const double* __restrict__ metric, int N, int C, float* __restrict__ out) {
+  PDL_ENTER();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double s = 1e-5;
   double dice = 0.0, iou = 0.0;
@@ -242,6 +246,7 @@ template <typename TL>
 __global__ void __launch_bounds__(256) metric_partials_kernel(const float* __restrict__ p, const TL* __restrict__ t,
                                                               long long vox, int C, float thr,
                                                               double* __restrict__ metric) {
+  PDL_ENTER();
   extern __shared__ float s_m[];     // [3*C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_m[i] = 0.f;
   __syncthreads();
@@ -278,6 +283,7 @@ __global__ void __launch_bounds__(256) metric_partials_kernel(const float* __res
 __global__ void loss_finalize_kernel(const double* __restrict__ part, int C, int terms,
                                      const float* __restrict__ alpha, float gamma, float alpha_f,
                                      float* __restrict__ loss, float* __restrict__ lcoef) {
+  PDL_ENTER();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double s = 1e-5, eps = 1e-7;
   double val = 0.0;
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(256) loss_bwd_binary_kernel(const float* __res
                                                               const float* __restrict__ lcoef,
                                                               const float* __restrict__ gscale,
                                                               float* __restrict__ dz) {
+  PDL_ENTER();
   const float a = lcoef[0], b = lcoef[1], cs = lcoef[2], fs = lcoef[3], gamma = lcoef[4];
   const float gs = gscale[0];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
@@ -368,6 +375,7 @@ __global__ void __launch_bounds__(256) loss_bwd_multi_kernel(const float* __rest
                                                              const float* __restrict__ lcoef,
                                                              const float* __restrict__ gscale,
                                                              float* __restrict__ dz) {
+  PDL_ENTER();
   float a[C], b[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) {
@@ -420,6 +428,7 @@ __global__ void __launch_bounds__(256) loss_bwd_multi_generic_kernel(const float
                                                                      const float* __restrict__ lcoef,
                                                                      const float* __restrict__ gscale,
                                                                      float* __restrict__ dz) {
+  PDL_ENTER();
   const float cs = lcoef[2 * C], fs = lcoef[2 * C + 1], gamma = lcoef[2 * C + 2];
   const float gs = gscale[0];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox;
@@ -479,20 +488,20 @@ int loss_partials(const float* logits, const void* labels, int label_dtype, int 
   switch (C) {
     case 1:
       if (label_dtype == B200SEG_F32)
-        loss_partials_binary_kernel<float><<<grid, 256, 0, s>>>(logits, static_cast<const float*>(labels), vox, gamma,
+        launch_k(loss_partials_binary_kernel<float>, grid, 256, 0, s, logits, static_cast<const float*>(labels), vox, gamma,
                                                                 alpha_f, part, metric);
       else
-        loss_partials_binary_kernel<long long><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, alpha_f, part, metric);
+        launch_k(loss_partials_binary_kernel<long long>, grid, 256, 0, s, logits, tl, vox, gamma, alpha_f, part, metric);
       break;
-    case 2: loss_partials_multi_kernel<2><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
-    case 3: loss_partials_multi_kernel<3><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
-    case 4: loss_partials_multi_kernel<4><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
-    case 5: loss_partials_multi_kernel<5><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
-    case 6: loss_partials_multi_kernel<6><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
-    case 7: loss_partials_multi_kernel<7><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
-    case 8: loss_partials_multi_kernel<8><<<grid, 256, 0, s>>>(logits, tl, vox, gamma, part, metric); break;
+    case 2: launch_k(loss_partials_multi_kernel<2>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
+    case 3: launch_k(loss_partials_multi_kernel<3>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
+    case 4: launch_k(loss_partials_multi_kernel<4>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
+    case 5: launch_k(loss_partials_multi_kernel<5>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
+    case 6: launch_k(loss_partials_multi_kernel<6>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
+    case 7: launch_k(loss_partials_multi_kernel<7>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
+    case 8: launch_k(loss_partials_multi_kernel<8>, grid, 256, 0, s, logits, tl, vox, gamma, part, metric); break;
     default:
-      loss_partials_multi_generic_kernel<<<grid, 256, (5 * C + 3) * sizeof(float), s>>>(logits, tl, vox, C, gamma,
+      launch_k(loss_partials_multi_generic_kernel, grid, 256, (5 * C + 3) * sizeof(float), s, logits, tl, vox, C, gamma,
                                                                                         part, metric);
   }
   B200_LAUNCH_CHECK();
@@ -504,24 +513,23 @@ int metric_partials(const float* probs, const void* labels, int label_dtype, int
   B200_CHECK_ARG(C >= 1 && C <= 1024 && N >= 1 && N <= 65535, "metric_partials: unsupported shape");
   const dim3 grid = sample_grid(vox, N, device);
   if (label_dtype == B200SEG_F32)
-    metric_partials_kernel<float><<<grid, 256, 3 * C * sizeof(float), s>>>(probs, static_cast<const float*>(labels),
+    launch_k(metric_partials_kernel<float>, grid, 256, 3 * C * sizeof(float), s, probs, static_cast<const float*>(labels),
                                                                            vox, C, thr, metric);
   else
-    metric_partials_kernel<long long><<<grid, 256, 3 * C * sizeof(float), s>>>(
-        probs, static_cast<const long long*>(labels), vox, C, thr, metric);
+    launch_k(metric_partials_kernel<long long>, grid, 256, 3 * C * sizeof(float), s, probs, static_cast<const long long*>(labels), vox, C, thr, metric);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
 int metric_finalize(const double* metric, int N, int C, float* out, cudaStream_t s) {
-  metric_finalize_kernel<<<1, 32, 0, s>>>(metric, N, C, out);
+  launch_k(metric_finalize_kernel, 1, 32, 0, s, metric, N, C, out);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
 int loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f, float* loss,
                   float* lcoef, cudaStream_t s) {
-  loss_finalize_kernel<<<1, 32, 0, s>>>(part, C, terms, alpha, gamma, alpha_f, loss, lcoef);
+  launch_k(loss_finalize_kernel, 1, 32, 0, s, part, C, terms, alpha, gamma, alpha_f, loss, lcoef);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -536,20 +544,20 @@ int loss_bwd(const float* logits, const void* labels_, int label_dtype, long lon
   switch (C) {
     case 1:
       if (label_dtype == B200SEG_F32)
-        loss_bwd_binary_kernel<float><<<blocks, 256, 0, s>>>(logits, static_cast<const float*>(labels_), nvox_, lcoef,
+        launch_k(loss_bwd_binary_kernel<float>, blocks, 256, 0, s, logits, static_cast<const float*>(labels_), nvox_, lcoef,
                                                              gscale, dlogits);
       else
-        loss_bwd_binary_kernel<long long><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits);
+        launch_k(loss_bwd_binary_kernel<long long>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits);
       break;
-    case 2: loss_bwd_multi_kernel<2><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
-    case 3: loss_bwd_multi_kernel<3><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
-    case 4: loss_bwd_multi_kernel<4><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
-    case 5: loss_bwd_multi_kernel<5><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
-    case 6: loss_bwd_multi_kernel<6><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
-    case 7: loss_bwd_multi_kernel<7><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
-    case 8: loss_bwd_multi_kernel<8><<<blocks, 256, 0, s>>>(logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 2: launch_k(loss_bwd_multi_kernel<2>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 3: launch_k(loss_bwd_multi_kernel<3>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 4: launch_k(loss_bwd_multi_kernel<4>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 5: launch_k(loss_bwd_multi_kernel<5>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 6: launch_k(loss_bwd_multi_kernel<6>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 7: launch_k(loss_bwd_multi_kernel<7>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
+    case 8: launch_k(loss_bwd_multi_kernel<8>, blocks, 256, 0, s, logits, labels, nvox_, lcoef, gscale, dlogits); break;
     default:
-      loss_bwd_multi_generic_kernel<<<blocks, 256, 0, s>>>(logits, labels, nvox_, C, lcoef, gscale, dlogits);
+      launch_k(loss_bwd_multi_generic_kernel, blocks, 256, 0, s, logits, labels, nvox_, C, lcoef, gscale, dlogits);
   }
   B200_LAUNCH_CHECK();
   return B200SEG_OK;

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(PW_THREADS, UP ? 1 : 2)
                        const float* __restrict__ bias, bf16* __restrict__ y, long long yld,
                        const bf16* __restrict__ addend, long long ald, double* __restrict__ stats, long long NV,
                        long long V, int D, int H, int W, int ud) {
+  PDL_ENTER();
   constexpr int XP = CIN * 2 + 16;                 // smem row pitch (bytes)
   constexpr int KS = CIN / 16, NT = COUT / 8;
   constexpr int XCH = CIN / 8;                     // 16-byte chunks per voxel
@@ -259,8 +260,7 @@ static int pw_launch(int dims, const b200seg_tensor* x, const void* w, const flo
   const long long tiles = NV / PW_TILE;
   long long grid = (long long)num_sms(device) * (UP ? 1 : 2);
   if (grid > tiles) grid = tiles;
-  pw_conv_mma_kernel<CIN, COUT, UP><<<(unsigned)grid, PW_THREADS, smem, st>>>(
-      static_cast<const bf16*>(x->ptr), x->ld, static_cast<const bf16*>(w), bias, static_cast<bf16*>(y->ptr), y->ld,
+  launch_k(pw_conv_mma_kernel<CIN, COUT, UP>, (unsigned)grid, PW_THREADS, smem, st, static_cast<const bf16*>(x->ptr), x->ld, static_cast<const bf16*>(w), bias, static_cast<bf16*>(y->ptr), y->ld,
       addend ? static_cast<const bf16*>(addend->ptr) : nullptr, addend ? addend->ld : 0, stats, NV, V, x->d, x->h,
       x->w, dims == 3 ? 2 : 1);
   B200_LAUNCH_CHECK();

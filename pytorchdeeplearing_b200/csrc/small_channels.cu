@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) conv_smallcin_kernel(const TX* __restrict
                                                             TY* __restrict__ y, long long yld,
                                                             double* __restrict__ stats, int D, int H, int W, int Cin,
                                                             int kd, int kh, int kw, int pd, int ph, int pw) {
+  PDL_ENTER();
   extern __shared__ float s_w[];                  // [taps*Cin][COUT] + [COUT] bias + stats scratch
   const int taps = kd * kh * kw;
   const int nw = taps * Cin * COUT;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) wgrad_smallcin_kernel(const TA* __restric
                                                              const TB* __restrict__ b, long long bld,
                                                              float* __restrict__ dwp, int N, int D, int H, int W,
                                                              int Cin, int kd, int kh, int kw, int pd, int ph, int pw) {
+  PDL_ENTER();
   __shared__ float s_red[8][32][COUT + 1];
   const int taps = kd * kh * kw;
   const int R = taps * Cin;
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const TX* __restrict__ x,
                                                        const float* __restrict__ w /*[NC][Cin]*/,
                                                        const float* __restrict__ bias, float* __restrict__ logits,
                                                        float* __restrict__ probs, long long NV) {
+  PDL_ENTER();
   extern __shared__ float s_hw[];                 // [NC][Cin] + [NC]
   for (int i = threadIdx.x; i < NC * Cin; i += blockDim.x) s_hw[i] = w[i];
   for (int i = threadIdx.x; i < NC; i += blockDim.x) s_hw[NC * Cin + i] = bias ? bias[i] : 0.f;
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const TX* __restrict__ x,
                                                        const float* __restrict__ dl, const float* __restrict__ w,
                                                        TX* __restrict__ dx, long long dxld, float* __restrict__ dw,
                                                        float* __restrict__ db, long long NV) {
+  PDL_ENTER();
   __shared__ float s_hw[NC * CIN];
   __shared__ float s_acc[8][NC * CIN + NC];
   for (int i = threadIdx.x; i < NC * CIN; i += blockDim.x) s_hw[i] = w[i];
@@ -345,7 +349,7 @@ static int smallcin_conv_typed(const ConvGeom& g, const b200seg_tensor* x, const
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, x->n);
 #define LAUNCH_SC(CO)                                                                                              \
-  conv_smallcin_kernel<TX, TW, TY, CO><<<grid, 256, (taps * x->c * CO + CO + 8 * 2 * CO) * sizeof(float), st>>>(   \
+  launch_k(conv_smallcin_kernel<TX, TW, TY, CO>, grid, 256, (taps * x->c * CO + CO + 8 * 2 * CO) * sizeof(float), st, \
       static_cast<const TX*>(x->ptr), x->ld, static_cast<const TW*>(w), bias, static_cast<TY*>(y->ptr), y->ld,     \
       stats, x->d, x->h, x->w, x->c, g.kd, g.kh, g.kw, g.pd, g.ph, g.pw)
   switch (y->c) {
@@ -390,7 +394,7 @@ static int smallcin_wgrad_typed(const ConvGeom& g, const b200seg_tensor* a, cons
   long long grid = (long long)num_sms(device) * 8;
   if (grid > NV) grid = NV;
 #define LAUNCH_SW(CO)                                                                                        \
-  wgrad_smallcin_kernel<TA, TB, CO><<<(unsigned)grid, 256, 0, st>>>(                                         \
+  launch_k(wgrad_smallcin_kernel<TA, TB, CO>, (unsigned)grid, 256, 0, st, \
       static_cast<const TA*>(a->ptr), a->ld, static_cast<const TB*>(b->ptr), b->ld, dwp, b->n, b->d, b->h,   \
       b->w, a->c, g.kd, g.kh, g.kw, g.pd, g.ph, g.pw)
   switch (b->c) {
@@ -428,7 +432,7 @@ static int head_fwd_typed(const b200seg_tensor* x, const float* w, const float* 
   const int blocks = head_blocks(NV, device);
   const size_t sm = (size_t)(nc * x->c + nc) * sizeof(float);
 #define LAUNCH_HF(NC) \
-  head_fwd_kernel<TX, NC><<<blocks, 256, sm, st>>>(static_cast<const TX*>(x->ptr), x->ld, x->c, w, bias, logits, probs, NV)
+  launch_k(head_fwd_kernel<TX, NC>, blocks, 256, sm, st, static_cast<const TX*>(x->ptr), x->ld, x->c, w, bias, logits, probs, NV)
   switch (nc) {
     case 1: LAUNCH_HF(1); break;
     case 2: LAUNCH_HF(2); break;
@@ -459,7 +463,7 @@ static int head_bwd_cin(const b200seg_tensor* x, const float* dl, const float* w
   const long long NV = (long long)x->n * x->d * x->h * x->w;
   const int blocks = head_blocks(NV, device) / 2 + 1;
 #define LAUNCH_HB(NC)                                                                                          \
-  head_bwd_kernel<TX, NC, CIN><<<blocks, 256, 0, st>>>(static_cast<const TX*>(x->ptr), x->ld, dl, w,           \
+  launch_k(head_bwd_kernel<TX, NC, CIN>, blocks, 256, 0, st, static_cast<const TX*>(x->ptr), x->ld, dl, w,           \
                                                        static_cast<TX*>(dx->ptr), dx->ld, dw, db, NV)
   switch (nc) {
     case 1: LAUNCH_HB(1); break;

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256, 2) conv_stem1_kernel(const TX* __restrict
                                                             const TW* __restrict__ w, const float* __restrict__ bias,
                                                             TY* __restrict__ y, long long yld,
                                                             double* __restrict__ stats, int D, int H, int W) {
+  PDL_ENTER();
   constexpr int TAPS = KD * KHW * KHW;
   constexpr int PD = KD / 2, PHW = KHW / 2;
   constexpr int XW = KHW + VPT - 1;                 // input columns covering the thread's VPT voxels along w
@@ -152,6 +153,7 @@ template <typename TA, typename TB, int COUT, int KD, int KHW, int CG>
 __global__ void __launch_bounds__(256) wgrad_stem1_kernel(const TA* __restrict__ a, long long ald,
                                                           const TB* __restrict__ b, long long bld,
                                                           float* __restrict__ dwp, int N, int D, int H, int W) {
+  PDL_ENTER();
   constexpr int PD = KD / 2, PHW = KHW / 2;
   constexpr int NCG = COUT / CG;
   constexpr int NVAR = KD * NCG;
@@ -265,11 +267,11 @@ static int stem_conv_co(int kind, int dims, const b200seg_tensor* x, const void*
 #define STEM_LAUNCH(KD_, KHW_)                                                                                     \
   do {                                                                                                             \
     if (vpt == 2)                                                                                                  \
-      conv_stem1_kernel<TX, TW, TY, CO, KD_, KHW_, 2><<<grid, 256, 0, st>>>(                                       \
+      launch_k(conv_stem1_kernel<TX, TW, TY, CO, KD_, KHW_, 2>, grid, 256, 0, st, \
           static_cast<const TX*>(x->ptr), x->ld, static_cast<const TW*>(w), bias, static_cast<TY*>(y->ptr), y->ld, \
           stats, x->d, x->h, x->w);                                                                                \
     else                                                                                                           \
-      conv_stem1_kernel<TX, TW, TY, CO, KD_, KHW_, 1><<<grid, 256, 0, st>>>(                                       \
+      launch_k(conv_stem1_kernel<TX, TW, TY, CO, KD_, KHW_, 1>, grid, 256, 0, st, \
           static_cast<const TX*>(x->ptr), x->ld, static_cast<const TW*>(w), bias, static_cast<TY*>(y->ptr), y->ld, \
           stats, x->d, x->h, x->w);                                                                                \
   } while (0)
@@ -321,7 +323,7 @@ static int stem_wgrad_co(int kind, int dims, const b200seg_tensor* a, const b200
     const long long need = (NV + 255) / 256;                                                                       \
     if (nch > need) nch = need;                                                                                    \
     if (nch < 1) nch = 1;                                                                                          \
-    wgrad_stem1_kernel<TA, TB, CO, KD_, KHW_, CG_><<<(unsigned)(nch * nvar), 256, 0, st>>>(                        \
+    launch_k(wgrad_stem1_kernel<TA, TB, CO, KD_, KHW_, CG_>, (unsigned)(nch * nvar), 256, 0, st, \
         static_cast<const TA*>(a->ptr), a->ld, static_cast<const TB*>(b->ptr), b->ld, dwp, b->n, b->d, b->h,       \
         b->w);                                                                                                     \
   } while (0)

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     conv_stem_mma_kernel(const TA* __restrict__ x, const bf16* __restrict__ w /*[taps][COUT]*/,
                          const float* __restrict__ bias, bf16* __restrict__ y, long long yld,
                          double* __restrict__ stats, const StemGeom g) {
+  PDL_ENTER();
   constexpr int TAPS = KD * KHW * KHW;
   constexpr int PAD = KHW / 2;
   constexpr int KS = (TAPS + 15) / 16;
@@ -263,6 +264,7 @@ template <typename TA, int COUT, int KD, int KHW>
 __global__ void __launch_bounds__(SM_THREADS, 2)
     wgrad_stem_mma_kernel(const TA* __restrict__ x, const bf16* __restrict__ dy, long long bld,
                           float* __restrict__ dwp /*[taps][COUT]*/, const StemGeom g) {
+  PDL_ENTER();
   constexpr int TAPS = KD * KHW * KHW;
   constexpr int PAD = KHW / 2;
   constexpr int NT = (TAPS + 7) / 8;         // n-tiles of 8 taps
@@ -447,7 +449,7 @@ static int stem_mma_conv_co(int kind, int dims, const b200seg_tensor* x, const v
 #define SMC_LAUNCH(KD_, KHW_)                                                                                     \
   do {                                                                                                            \
     const size_t smem = stem_x_bytes<KD_, KHW_ / 2>(g.TW) + (size_t)8 * 2 * CO * sizeof(float);                   \
-    conv_stem_mma_kernel<TA, CO, KD_, KHW_><<<grid, SM_THREADS, smem, st>>>(                                      \
+    launch_k(conv_stem_mma_kernel<TA, CO, KD_, KHW_>, grid, SM_THREADS, smem, st, \
         static_cast<const TA*>(x->ptr), static_cast<const bf16*>(w), bias, static_cast<bf16*>(y->ptr), y->ld,     \
         stats, g);                                                                                                \
   } while (0)
@@ -497,7 +499,7 @@ static int stem_mma_wgrad_co(int kind, int dims, const b200seg_tensor* a, const 
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));                   \
       attr_done[device] = 1;                                                                                      \
     }                                                                                                             \
-    wgrad_stem_mma_kernel<TA, CO, KD_, KHW_><<<grid, SM_THREADS, smem, st>>>(                                     \
+    launch_k(wgrad_stem_mma_kernel<TA, CO, KD_, KHW_>, grid, SM_THREADS, smem, st, \
         static_cast<const TA*>(a->ptr), static_cast<const bf16*>(b->ptr), b->ld, dwp, g);                         \
   } while (0)
   if (kind == B200SEG_K1) SMW_LAUNCH(1, 1);

@@ -21,6 +21,7 @@ namespace b200seg {
 // The step count lives on the device so that the update can be replayed from a CUDA graph.
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_tick_kernel(float* __restrict__ state, float lr, float beta1, float beta2) {
+  PDL_ENTER();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double t = (double)state[0] + 1.0;
   state[0] = (float)t;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
                                                         const float* __restrict__ state, float lr, float beta1,
                                                         float beta2, float eps, float wd, int decoupled,
                                                         const float* __restrict__ gscale, long long n4) {
+  PDL_ENTER();
   const float step_size = state[1], bc2s = state[2];
   const float gs = gscale ? gscale[0] : 1.f;
   const float decay = 1.f - lr * wd;
@@ -77,13 +79,13 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float* 
               cudaStream_t s) {
   const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                     reinterpret_cast<uintptr_t>(v)) % 16) == 0;
-  if (tick) adam_tick_kernel<<<1, 32, 0, s>>>(state, lr, beta1, beta2);
+  if (tick) launch_k(adam_tick_kernel, 1, 32, 0, s, state, lr, beta1, beta2);
   const long long n4 = al ? (n >> 2) : 0;         // unaligned slices (per-parameter calls) take the scalar loop
   long long blocks = ((al ? n / 4 : n) + 255) / 256;
   const long long cap = (long long)num_sms(device) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adam_step_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, n, state, lr, beta1, beta2, eps, wd, decoupled, gscale,
+  launch_k(adam_step_kernel, (int)blocks, 256, 0, s, p, g, m, v, n, state, lr, beta1, beta2, eps, wd, decoupled, gscale,
                                                n4);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -103,6 +105,7 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float* 
 __global__ void __launch_bounds__(256) dropout_masks_kernel(const long long* __restrict__ rng,
                                                             const int* __restrict__ table, int nmasks, int total,
                                                             double keep, float scale, float* __restrict__ out) {
+  PDL_ENTER();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int k = 0;
@@ -119,7 +122,7 @@ int dropout_masks(const long long* rng, const int* table, int nmasks, int total,
                   cudaStream_t s) {
   B200_CHECK_ARG(nmasks >= 1 && total >= 1 && p_drop >= 0.0 && p_drop < 1.0, "b200seg_dropout_masks: bad argument");
   const double keep = 1.0 - p_drop;
-  dropout_masks_kernel<<<(total + 255) / 256, 256, 0, s>>>(rng, table, nmasks, total, keep, (float)(1.0 / keep), out);
+  launch_k(dropout_masks_kernel, (total + 255) / 256, 256, 0, s, rng, table, nmasks, total, keep, (float)(1.0 / keep), out);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -148,6 +151,7 @@ template <typename TX, int NC>
 __global__ void __launch_bounds__(256) head_mask_kernel(const TX* __restrict__ x, long long xld, int Cin,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         unsigned char* __restrict__ mask, long long NV, float thr) {
+  PDL_ENTER();
   extern __shared__ float s_hw[];                 // [NC][Cin] + [NC]
   for (int i = threadIdx.x; i < NC * Cin; i += blockDim.x) s_hw[i] = w[i];
   for (int i = threadIdx.x; i < NC; i += blockDim.x) s_hw[NC * Cin + i] = bias ? bias[i] : 0.f;
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(256) head_mask_kernel(const TX* __restrict__ x
 
 __global__ void __launch_bounds__(256) mask_logits_kernel(const float* __restrict__ z, long long NV, int C, float thr,
                                                           unsigned char* __restrict__ mask) {
+  PDL_ENTER();
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < NV; v += (long long)gridDim.x * blockDim.x) {
     const float* zi = z + v * C;
     if (C == 1) {
@@ -205,7 +210,7 @@ static int head_mask_typed(const b200seg_tensor* x, const float* w, const float*
   const int blocks = mask_blocks(NV, device);
   const size_t smem = (size_t)(nc * x->c + nc) * sizeof(float);
 #define LAUNCH_HM(NC)                                                                                              \
-  head_mask_kernel<TX, NC><<<blocks, 256, smem, st>>>(static_cast<const TX*>(x->ptr), x->ld, x->c, w, bias, mask, \
+  launch_k(head_mask_kernel<TX, NC>, blocks, 256, smem, st, static_cast<const TX*>(x->ptr), x->ld, x->c, w, bias, mask, \
                                                       NV, thr)
   switch (nc) {
     case 1: LAUNCH_HM(1); break;
@@ -233,7 +238,7 @@ int head_mask(const b200seg_tensor* x, const float* w, const float* bias, unsign
 }
 
 int mask_logits(const float* logits, long long nv, int C, float thr, unsigned char* mask, int device, cudaStream_t st) {
-  mask_logits_kernel<<<mask_blocks(nv, device), 256, 0, st>>>(logits, nv, C, thr, mask);
+  launch_k(mask_logits_kernel, mask_blocks(nv, device), 256, 0, st, logits, nv, C, thr, mask);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

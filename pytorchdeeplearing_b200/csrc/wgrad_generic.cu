@@ -28,6 +28,7 @@ struct WgradArgs {
 
 template <typename TA, typename TB, int BB>
 __global__ void __launch_bounds__(256) wgrad_ffma_kernel(const WgradArgs<TA, TB> w) {
+  PDL_ENTER();
   constexpr int BA = 4096 / BB;
   constexpr int BV = 16;
   constexpr int AQ = BA / 4;           // A quads per voxel row
@@ -219,9 +220,9 @@ static int wgrad_typed(int kind, int dims, const b200seg_tensor* a, const b200se
   w.steps_per_chunk = (int)((total_steps + chunks - 1) / chunks);
   chunks = (total_steps + w.steps_per_chunk - 1) / w.steps_per_chunk;
   dim3 grid(gx, gy, (unsigned)chunks), block(256);
-  if (BB == 16) wgrad_ffma_kernel<TA, TB, 16><<<grid, block, 0, st>>>(w);
-  else if (BB == 32) wgrad_ffma_kernel<TA, TB, 32><<<grid, block, 0, st>>>(w);
-  else wgrad_ffma_kernel<TA, TB, 64><<<grid, block, 0, st>>>(w);
+  if (BB == 16) launch_k(wgrad_ffma_kernel<TA, TB, 16>, grid, block, 0, st, w);
+  else if (BB == 32) launch_k(wgrad_ffma_kernel<TA, TB, 32>, grid, block, 0, st, w);
+  else launch_k(wgrad_ffma_kernel<TA, TB, 64>, grid, block, 0, st, w);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

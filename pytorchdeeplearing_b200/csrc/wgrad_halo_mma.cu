@@ -42,6 +42,7 @@ template <int CIN, int COUT, int TW, int TPW, int S>
 __global__ void __launch_bounds__(32 * (27 / TPW) * S, 1)
     wgrad_halo_mma_kernel(const bf16* __restrict__ x, long long xld, const bf16* __restrict__ dy, long long bld,
                           float* __restrict__ dwp, const WhGeom g) {
+  PDL_ENTER();
   constexpr int R = 27 / TPW;                       // tap groups (warp roles)
   constexpr int NTHREADS = 32 * R * S;
   constexpr int XP = CIN * 2 + 16;                  // bytes per voxel row of the x tile (16 B pad: bank spread)
@@ -232,8 +233,7 @@ static int wh_launch(const b200seg_tensor* a, const b200seg_tensor* b, float* dw
   }
   const int sms = num_sms(device);
   const int grid = g.tiles < sms ? g.tiles : sms;
-  wgrad_halo_mma_kernel<CIN, COUT, TW, TPW, S><<<grid, 32 * (27 / TPW) * S, smem, st>>>(
-      static_cast<const bf16*>(a->ptr), a->ld, static_cast<const bf16*>(b->ptr), b->ld, dwp, g);
+  launch_k(wgrad_halo_mma_kernel<CIN, COUT, TW, TPW, S>, grid, 32 * (27 / TPW) * S, smem, st, static_cast<const bf16*>(a->ptr), a->ld, static_cast<const bf16*>(b->ptr), b->ld, dwp, g);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

@@ -36,6 +36,7 @@ constexpr int kWgMaxStages = 6;
 
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, const WgArgs p) {
+  PDL_ENTER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t A_SUB = 128u * (uint32_t)p.CA * 2u;          // bytes of one A sub-tile
@@ -319,7 +320,7 @@ int wgrad_tc(int kind, int dims, const b200seg_tensor* a, const b200seg_tensor* 
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid(gx, gy);
-  wgrad_tc_kernel<<<grid, 192, smem_bytes, st>>>(tmA, tmB, p);
+  launch_k(wgrad_tc_kernel, grid, 192, smem_bytes, st, tmA, tmB, p);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

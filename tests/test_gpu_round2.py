@@ -153,7 +153,8 @@ def test_graph_replay_equals_eager_and_steps_the_optimizer(train):
     assert abs(loss_g.item() - loss_e.item()) < 1e-6
     assert abs(step.dice.item() - dice_e) < 1e-6
     for n, p in model.named_parameters():
-        assert torch.equal(p.grad, ref[n]), n                  # same kernels, same order: bit-identical
+        # same kernels in the same order; the split-K weight gradients end in fp32 atomics, so not bit-identical
+        assert (p.grad - ref[n]).norm() <= 2e-5 * ref[n].norm() + 1e-12, n
     for p in model.parameters():
         p.grad = None                                          # zero_grad(set_to_none=True)
     step(xc, yc)
