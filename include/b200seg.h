@@ -151,7 +151,8 @@ int b200seg_apply_gn(const b200seg_tensor* y1, const b200seg_gn* gn1, const b200
                      const b200seg_tensor* res, const b200seg_tensor* out, int device, b200seg_stream stream);
 int b200seg_gn_bwd_reduce_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, double* sums,
                              int device, b200seg_stream stream);
-/* dy as b200seg_gn_bwd_apply; additionally dgamma[c] +=, dbeta[c] +=, dbias[c] = (dbias may be NULL) */
+/* dy as b200seg_gn_bwd_apply; additionally dgamma[c] +=, dbeta[c] +=, dbias[c] += (dbias may be NULL; fp32 atomics
+ * over the samples: the caller zero-fills the gradient bucket) */
 int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, const double* sums,
                             const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int device,
                             b200seg_stream stream);

@@ -751,6 +751,28 @@ __global__ void gn_bwd_finalize_kernel(const double* __restrict__ sums, const fl
   }
 }
 
+// d gamma, d beta, d bias of ONE sample from the coefficients a CTA has just derived for it with
+// gn_cta_coefs<true> (grp = {mean, rstd, m1, m2} per group; s_f = scale, gamma, beta per channel): the three
+// parameter gradients are sums over the batch, added with fp32 atomics (the gradient bucket is zero on entry).
+__device__ __forceinline__ void param_grads_of_sample(const GnRef& gn, const double* __restrict__ sums,
+                                                      const double* grp, const float* s_f, int n, int C,
+                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                      float* __restrict__ dbias) {
+  const int cpg = C / gn.groups;
+  const double vox = gn.m / (double)cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mu = grp[g * 4 + 0], rs = grp[g * 4 + 1], m1 = grp[g * 4 + 2], m2 = grp[g * 4 + 3];
+    const double sc = (double)s_f[c], ga = (double)s_f[C + c];
+    const double* sp = sums + ((long long)n * C + c) * 3;
+    const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
+    const double qd = -rs * rs * m2, rd = -rs * m1 + rs * rs * mu * m2;
+    atomicAdd(dbeta + c, (float)s1);
+    atomicAdd(dgamma + c, (float)(rs * (s2 - mu * s1)));
+    if (dbias != nullptr) atomicAdd(dbias + c, (float)(rs * ga * s1 + qd * s3 + rd * vox));
+  }
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const T* __restrict__ g, long long ldg,
                                                            const T* __restrict__ y, long long ldy,
@@ -768,34 +790,11 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const T* __restric
     double* s_d = s_dyn;
     float* s_f = reinterpret_cast<float*>(s_d + gn_cta_doubles(C, gn.groups, true));
     float* s_c5 = s_f + 3 * C;                            // [5][C]: A, B, P, Q, R
-    // parameter gradients (d gamma, d beta, d bias): the LAST block of the grid, fixed order over the samples
-    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) {
-      const int cpg = C / gn.groups;
-      const double vox = gn.m / (double)cpg;
-      double dg[2] = {0.0, 0.0}, db[2] = {0.0, 0.0}, dbi[2] = {0.0, 0.0};      // channels tid, tid + 256
-      for (int nn = 0; nn < N; ++nn) {
-        const double* grp = gn_cta_coefs<true>(gn, sums, nn, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C,
-                                               s_c5 + 4 * C);
-        for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
-          const int g = c / cpg;
-          const double mu = grp[g * 4 + 0], rs = grp[g * 4 + 1], m1 = grp[g * 4 + 2], m2 = grp[g * 4 + 3];
-          const double sc = (double)s_f[c], ga = (double)s_f[C + c];
-          const double* sp = sums + ((long long)nn * C + c) * 3;
-          const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
-          const double qd = -rs * rs * m2, rd = -rs * m1 + rs * rs * mu * m2;
-          db[k] += s1;
-          dg[k] += rs * (s2 - mu * s1);
-          dbi[k] += rs * ga * s1 + qd * s3 + rd * vox;
-        }
-        __syncthreads();
-      }
-      for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
-        dgamma[c] += (float)dg[k];
-        dbeta[c] += (float)db[k];
-        if (dbias != nullptr) dbias[c] = (float)dbi[k];
-      }
-    }
-    gn_cta_coefs<true>(gn, sums, n, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C, s_c5 + 4 * C);
+    const double* grp = gn_cta_coefs<true>(gn, sums, n, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C,
+                                           s_c5 + 4 * C);
+    // parameter gradients (d gamma, d beta, d bias): ONE block per sample adds its sample's share from the
+    // coefficients it has just derived (no serial loop over the batch at the tail of the grid); fp32 atomics over N
+    if (blockIdx.x == gridDim.x - 1) param_grads_of_sample(gn, sums, grp, s_f, n, C, dgamma, dbeta, dbias);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       A[j] = s_c5[c0 + j];
@@ -928,33 +927,9 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const T* __restric
   __syncthreads();
   // ---------------------------------------------------------------- phase 2: dy and the parameter gradients
   float P[VEC], Q[VEC], R[VEC];
-  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) {
-    const int cpg = C / gn.groups;
-    const double vox = gn.m / (double)cpg;
-    double dg[2] = {0.0, 0.0}, db[2] = {0.0, 0.0}, dbi[2] = {0.0, 0.0};      // channels tid, tid + 256
-    for (int nn = 0; nn < N; ++nn) {
-      const double* grp = gn_cta_coefs<true>(gn, sums, nn, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C,
-                                             s_c5 + 4 * C);
-      for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
-        const int gi_ = c / cpg;
-        const double mu = grp[gi_ * 4 + 0], rs = grp[gi_ * 4 + 1], m1 = grp[gi_ * 4 + 2], m2 = grp[gi_ * 4 + 3];
-        const double sc = (double)s_f[c], ga = (double)s_f[C + c];
-        const double* sp = sums + ((long long)nn * C + c) * 3;
-        const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
-        const double qd = -rs * rs * m2, rd = -rs * m1 + rs * rs * mu * m2;
-        db[k] += s1;
-        dg[k] += rs * (s2 - mu * s1);
-        dbi[k] += rs * ga * s1 + qd * s3 + rd * vox;
-      }
-      __syncthreads();
-    }
-    for (int c = threadIdx.x, k = 0; c < C && k < 2; c += blockDim.x, ++k) {
-      dgamma[c] += (float)dg[k];
-      dbeta[c] += (float)db[k];
-      if (dbias != nullptr) dbias[c] = (float)dbi[k];
-    }
-  }
-  gn_cta_coefs<true>(gn, sums, n, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C, s_c5 + 4 * C);
+  const double* grp = gn_cta_coefs<true>(gn, sums, n, C, s_d, s_f, s_c5, s_c5 + C, s_c5 + 2 * C, s_c5 + 3 * C,
+                                         s_c5 + 4 * C);
+  if (blockIdx.x == gridDim.x - 1) param_grads_of_sample(gn, sums, grp, s_f, n, C, dgamma, dbeta, dbias);
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     A[j] = s_c5[c0 + j];
@@ -1221,7 +1196,8 @@ int ew_apply(const b200seg_tensor* y1, const float* c1, const b200seg_gn* g1, co
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, out->n, device, 3), out->n);
     const int mg = (g1 && g2 && g2->groups > g1->groups) ? g2->groups : (g1 ? g1->groups : 1);
-    const size_t smem = gn_cta_doubles(C, mg, false) * sizeof(double) + (size_t)7 * C * sizeof(float);
+    // (precomputed-coefficient form: no coefficient scratch -- any channel count fits)
+    const size_t smem = (g1 && g1->stats) ? gn_cta_doubles(C, mg, false) * sizeof(double) + (size_t)7 * C * sizeof(float) : 0;
     launch_k(apply_kernel<T, VEC>, grid, 256, smem, s, static_cast<const T*>(y1->ptr), y1->ld, c1, y2 ? static_cast<const T*>(y2->ptr) : nullptr, y2 ? y2->ld : 0, c2,
         res ? static_cast<const T*>(res->ptr) : nullptr, res ? res->ld : 0, static_cast<T*>(out->ptr), out->ld, C, V,
         make_gnref(g1, C), make_gnref(g2, C));
@@ -1241,9 +1217,11 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
     dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
     const bool pow2g = (G & (G - 1)) == 0;
     const int groups = (gn && gn->stats) ? gn->groups : 1;
-    const size_t base = (3 * C + gn_cta_doubles(C, groups, false)) * sizeof(double) + (size_t)5 * C * sizeof(float);
-    const size_t staged_bytes = base + (size_t)8 * 3 * C * sizeof(float);
+    const size_t full = (3 * C + gn_cta_doubles(C, groups, false)) * sizeof(double) + (size_t)5 * C * sizeof(float);
+    const size_t staged_bytes = full + (size_t)8 * 3 * C * sizeof(float);
     const int staged = (pow2g && G <= 32 && staged_bytes <= 46 * 1024) ? 1 : 0;
+    // precomputed-coefficient form without staging: only the [3][C] fp64 accumulators are touched (wide nets)
+    const size_t base = (gn && gn->stats) ? full : (size_t)3 * C * sizeof(double);
     launch_k(gn_bwd_reduce_kernel<T, VEC>, grid, 256, staged ? staged_bytes : base, s, static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
         make_gnref(gn, C), staged);
   });
@@ -1275,7 +1253,7 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
     const int G = C / VEC;
     dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
     const int groups = (gn && gn->stats) ? gn->groups : 1;
-    const size_t smem = gn_cta_doubles(C, groups, true) * sizeof(double) + (size_t)8 * C * sizeof(float);
+    const size_t smem = (gn && gn->stats) ? gn_cta_doubles(C, groups, true) * sizeof(double) + (size_t)8 * C * sizeof(float) : 0;
     launch_k(gn_bwd_apply_kernel<T, VEC>, grid, 256, smem, s, static_cast<const T*>(g->ptr), g->ld,
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
                                                      static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
