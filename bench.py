@@ -692,6 +692,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline_sample()
         _emit(line)
     if world > 1:
+        del graphed                    # graphs first, then the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -384,6 +384,328 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Input-slice-major form of the 3-D kernel (KD = 3): every staged input slice is multiplied ONCE per (kh, kw, K chunk)
+// against the weights of all three kd taps side by side, B = [W(kd=2) | W(kd=1) | W(kd=0)] (N = 3*Cout columns), and
+// accumulates into the three output slices (i-2, i-1, i) it contributes to, which are neighbouring column ranges
+// of a TMEM ring of accumulators.  The M128 x N x K16 instruction is bound by the fetch of its A operand (128 voxel
+// rows re-read from shared memory per K step whatever N is: measured ~27 + 0.6*N cycles), so 9 instructions of
+// N = 3*Cout per input slice instead of 27 of N = Cout per output slice do the same MACs with a third of the A reads
+// (16 channels: 9 x ~57 instead of 27 x ~37 cycles per slice-tile; 32 channels: 18 x ~87 instead of 54 x ~47).
+//   * accumulators: ring of kAccRing slots of Cout columns; slot of output o = (running output count) % ring; an
+//     output is complete when the input slice two further on has been issued (commit -> tfull[slot]);
+//   * all MMAs accumulate (the instruction-wide accumulate flag cannot distinguish the fresh third of its columns):
+//     the epilogue hands a slot back ZEROED (tcgen05.st) and the whole ring is zeroed once at kernel start;
+//   * at the ends of an item's d-range the column range shrinks to the outputs that exist (N = Cout or 2*Cout,
+//     weight rows offset accordingly), and a range that would wrap around the ring is issued in two pieces;
+//   * the weight image in smem is the packed image permuted at load time to [(kh,kw)][Cin/8][kd reversed][Cout][8].
+// Loaders (cp.async, zero fill = conv padding), slice ring, epilogue arithmetic and statistics are those of
+// conv_halo_kernel above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAccRing = 8;
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloArgs p) {
+  PDL_ENTER();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  constexpr int KD = 3;
+  constexpr int CP = CIN / 8;                                // 8-channel planes
+  constexpr uint32_t PLANE = HP_H * HP_W * 16u;              // bytes of one plane of one slice
+  constexpr uint32_t SLICE = (uint32_t)CP * PLANE;
+  constexpr int taps = 27;
+  constexpr uint32_t W_BYTES = (uint32_t)taps * CIN * COUT * 2u;
+  constexpr int R = kAccRing;
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + ((W_BYTES + 127u) & ~127u);
+  uint8_t* tail = s_ring + (size_t)p.nslices * SLICE;
+  tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* sempty = sfull + kHaloMaxSlices;
+  uint64_t* tfull = sempty + kHaloMaxSlices;
+  uint64_t* tempty = tfull + R;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + R);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][2][Cout]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int items_per_cta = (p.nitems + gridDim.x - 1) / gridDim.x;
+  const int item_begin = blockIdx.x * items_per_cta;
+  const int item_end = min(p.nitems, item_begin + items_per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslices; ++s) {
+      mbar_init(&sfull[s], 32 * kLoaderWarps);   // cp.async loader: one (deferred) arrive per loader thread
+      mbar_init(&sempty[s], 1);                  // tcgen05.commit
+    }
+    for (int a = 0; a < R; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // resident weights: 16-byte granules of the packed image [tap = (kd,kh,kw)][plane][co] -> [(kh,kw)][plane][2-kd][co]
+  for (uint32_t g = threadIdx.x; g < W_BYTES / 16u; g += blockDim.x) {
+    const uint32_t co = g % COUT;
+    const uint32_t t1 = g / COUT;
+    const uint32_t plane = t1 % CP;
+    const uint32_t tap = t1 / CP;
+    const uint32_t kd = tap / 9u, t9 = tap - kd * 9u;
+    const uint32_t dst = ((t9 * CP + plane) * 3u + (2u - kd)) * COUT + co;
+    *reinterpret_cast<uint4*>(s_w + dst * 16u) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + g * 16u);
+  }
+  for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 1 && warp <= 4) {
+    // the accumulator ring starts at zero (every MMA accumulates)
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = 0; c < R * COUT; c += 16) tmem_st16_zero(trow + (uint32_t)c);
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  constexpr int pd = 1;
+
+  auto decode = [&](int item, int& n, int& h0, int& w0, int& d0, int& nd) {
+    int t = item;
+    const int dc = t % p.ndchunks; t /= p.ndchunks;
+    const int iw = t % p.tw; t /= p.tw;
+    const int ih = t % p.th;
+    n = t / p.th;
+    w0 = iw * HT_W;
+    h0 = ih * HT_H;
+    d0 = dc * p.dchunk;
+    nd = min(p.dchunk, p.D - d0);
+  };
+
+  if (warp == 0) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);   // | (N >> 3) << 17
+    const uint64_t a_hi = make_nosw_desc(0, PLANE, HP_W * 16u);
+    const uint64_t b_hi = make_nosw_desc(0, 3u * COUT * 16u, 128u);
+    const uint32_t ring_u32 = smem_u32(s_ring);
+    const uint32_t w_u32 = smem_u32(s_w);
+    constexpr int kchunks = CIN / 16;
+    uint32_t gs = 0;   // input slices consumed so far (ring position of the item's first slice)
+    uint32_t go = 0;   // output slices started so far (accumulator slot of the item's first output)
+    for (int item = item_begin; item < item_end; ++item) {
+      int n, h0, w0, d0, nd;
+      decode(item, n, h0, w0, d0, nd);
+      const int nsl = nd + KD - 1;
+      for (int i = 0; i < nsl; ++i) {
+        const uint32_t sl = gs + (uint32_t)i;
+        mbar_wait(&sfull[sl % p.nslices], (sl / p.nslices) & 1u);
+        if (i < nd) {
+          // output i is touched for the first time: its slot must have been drained (and zeroed) by the epilogue
+          const uint32_t gn_ = go + (uint32_t)i;
+          mbar_wait(&tempty[gn_ % R], ((gn_ / R) & 1u) ^ 1u);
+        }
+        // slices written by cp.async (generic proxy) must be ordered before the tensor core's async-proxy reads
+        fence_proxy_async();
+        tc_fence_after();
+        if (elect_one()) {
+          const int lo = i - 2 > 0 ? i - 2 : 0;
+          const int hi = i < nd - 1 ? i : nd - 1;
+          const uint64_t a_base = a_hi | (uint64_t)((ring_u32 + (sl % p.nslices) * SLICE) >> 4);
+          // pieces of [lo, hi] that are contiguous in the accumulator ring
+          int o0 = lo;
+          while (o0 <= hi) {
+            const uint32_t slot0 = (go + (uint32_t)o0) % R;
+            int cnt = hi - o0 + 1;
+            if ((int)slot0 + cnt > R) cnt = R - (int)slot0;
+            const uint32_t ncols = (uint32_t)cnt * COUT;
+            const uint32_t idesc = idesc0 | ((ncols >> 3) << 17);
+            const uint32_t tacc = tmem_base + slot0 * (uint32_t)COUT;
+            const uint32_t row0 = (uint32_t)(2 - i + o0) * COUT;            // weight rows: kd = i - o  ->  (2 - kd) * Cout
+            const uint64_t b_base = b_hi | (uint64_t)((w_u32 + row0 * 16u) >> 4);
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9)
+#pragma unroll
+              for (int kc = 0; kc < kchunks; ++kc) {
+                const uint32_t a_off = ((uint32_t)(2 * kc) * PLANE + (uint32_t)((t9 / 3) * HP_W + (t9 % 3)) * 16u) >> 4;
+                const uint32_t b_off = ((uint32_t)(t9 * CP + 2 * kc) * 3u * COUT * 16u) >> 4;
+                umma_bf16(tacc, a_base + a_off, b_base + b_off, idesc, 1u);
+              }
+            o0 += cnt;
+          }
+          if (i >= 2) umma_commit(&tfull[(go + (uint32_t)(i - 2)) % R]);   // output i-2 has all three contributions
+          umma_commit(&sempty[sl % p.nslices]);                            // this input slice is consumed
+        }
+        __syncwarp();
+      }
+      gs += (uint32_t)nsl;
+      go += (uint32_t)nd;
+    }
+  } else if (warp >= 5) {
+    // ===================================================== loaders (8 warps, cp.async, ring-deep prefetch)
+    constexpr int LT = 32 * kLoaderWarps;
+    const int lt = threadIdx.x - 160;
+    const int pieces = HP_H * HP_W * CP;
+    int poff[kMaxPieces], phh[kMaxPieces], pww[kMaxPieces];
+    bool pval[kMaxPieces];
+#pragma unroll
+    for (int j = 0; j < kMaxPieces; ++j) {
+      const int q = lt + j * LT;
+      pval[j] = q < pieces;
+      const int qq = pval[j] ? q : 0;
+      const int v = qq / CP, plane = qq - v * CP;
+      phh[j] = v / HP_W;
+      pww[j] = v - phh[j] * HP_W;
+      poff[j] = plane * (int)PLANE + v * 16;
+      pww[j] |= plane << 16;
+    }
+    int it_item = item_begin, it_i = 0, it_nsl = 0, n = 0, h0 = 0, w0 = 0, d0 = 0, nd = 0;
+    if (it_item < item_end) {
+      decode(it_item, n, h0, w0, d0, nd);
+      it_nsl = nd + KD - 1;
+    }
+    uint32_t sl = 0;
+    while (it_item < item_end) {
+      const uint32_t slot = sl % p.nslices;
+      mbar_wait(&sempty[slot], ((sl / p.nslices) & 1u) ^ 1u);
+      const uint32_t dst = smem_u32(s_ring + (size_t)slot * SLICE);
+      const int d = d0 - pd + it_i;
+      const bool dok = (unsigned)d < (unsigned)p.D;
+      const bf16* src = p.x + (((long long)n * p.D + (dok ? d : 0)) * p.H) * p.W * p.xld;
+#pragma unroll
+      for (int j = 0; j < kMaxPieces; ++j) {
+        if (!pval[j]) continue;
+        const int plane = pww[j] >> 16, ww = pww[j] & 0xffff;
+        const int h = h0 - 1 + phh[j], w = w0 - 1 + ww;
+        const bool ok = dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+        const bf16* g = ok ? src + ((long long)h * p.W + w) * p.xld + plane * 8 : p.x;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)poff[j]), "l"(g),
+                     "r"(ok ? 16 : 0)
+                     : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sfull[slot])) : "memory");
+      ++it_i;
+      if (it_i == it_nsl) {
+        ++it_item;
+        it_i = 0;
+        if (it_item < item_end) {
+          decode(it_item, n, h0, w0, d0, nd);
+          it_nsl = nd + KD - 1;
+        }
+      }
+      ++sl;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // ===================================================== epilogue warps 1..4
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rw = row % HT_W, rh = row / HT_W;
+    const int etid = (warp - 1) * 32 + lane;
+    uint32_t go = 0;
+    int cur_n = -1;
+    auto flush_stats = [&](int n) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.stats != nullptr && n >= 0) {
+        for (int i = etid; i < 2 * p.Cout; i += 128) {
+          const int which = i / p.Cout, c = i - which * p.Cout;
+          double t = 0.0;
+#pragma unroll
+          for (int wq = 0; wq < 4; ++wq) {
+            t += (double)s_stat[wq * 2 * p.Cout + i];
+            s_stat[wq * 2 * p.Cout + i] = 0.f;
+          }
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    for (int item = item_begin; item < item_end; ++item) {
+      int n, h0, w0, d0, nd;
+      decode(item, n, h0, w0, d0, nd);
+      if (n != cur_n) {
+        if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
+        cur_n = n;
+      }
+      const int oh = h0 + rh, ow = w0 + rw;
+      const bool valid = oh < p.H && ow < p.W;
+      for (int o = 0; o < nd; ++o, ++go) {
+        const long long vox = (((long long)n * p.D + (d0 + o)) * p.H + oh) * p.W + ow;
+        const uint32_t as = go % R;
+        mbar_wait(&tfull[as], (go / R) & 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * (uint32_t)COUT + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          float v[16];
+          tmem_ld16(tacc + (uint32_t)c0, v);
+          tmem_st16_zero(tacc + (uint32_t)c0);            // hand the columns back zeroed (all MMAs accumulate)
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+          }
+          if (p.stats != nullptr) {
+            float s[16], qq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              s[j] = valid ? v[j] : 0.f;
+              qq[j] = s[j] * s[j];
+            }
+#pragma unroll
+            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < half; ++j) {
+                const float keep_s = up ? s[j + half] : s[j];
+                const float send_s = up ? s[j] : s[j + half];
+                const float keep_q = up ? qq[j + half] : qq[j];
+                const float send_q = up ? qq[j] : qq[j + half];
+                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
+            }
+            s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+            qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+            if ((lane & 1) == 0) {
+              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              float* sw_ = s_stat + q * 2 * p.Cout;      // this warp's private row: no atomics, fixed order
+              sw_[c0 + col] += s[0];
+              sw_[p.Cout + c0 + col] += qq[0];
+            }
+          }
+          if (valid) {
+            if (p.addend != nullptr) {
+              float r[16];
+              load8(p.addend + vox * p.ald + c0, r);
+              load8(p.addend + vox * p.ald + c0 + 8, r + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += r[j];
+            }
+            store8(p.y + vox * p.yld + c0, v);
+            store8(p.y + vox * p.yld + c0 + 8, v + 8);
+          }
+          if (c0 + 16 >= COUT) {
+            // all columns of the slot are read and zeroed: the MMA issuer may start the next output in it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+          }
+        }
+      }
+    }
+    if (p.stats != nullptr && cur_n >= 0) flush_stats(cur_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 static bool al16h(const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
 
@@ -420,6 +742,10 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     HALO_ATTR(16, 16, 3); HALO_ATTR(16, 32, 3); HALO_ATTR(32, 16, 3); HALO_ATTR(32, 32, 3);
     HALO_ATTR(16, 16, 1); HALO_ATTR(16, 32, 1); HALO_ATTR(32, 16, 1); HALO_ATTR(32, 32, 1);
 #undef HALO_ATTR
+#define HALO3_ATTR(CI, CO) \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm))
+    HALO3_ATTR(16, 16); HALO3_ATTR(16, 32); HALO3_ATTR(32, 16); HALO3_ATTR(32, 32);
+#undef HALO3_ATTR
     g_halo_init[device] = 1;
   }
   HaloArgs p;
@@ -449,13 +775,18 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.nitems = cols * p.ndchunks;
   const uint32_t slice = (uint32_t)(p.Cin / 8) * HP_H * HP_W * 16u;
   const uint32_t wbytes = ((uint32_t)(p.kd * 9) * p.Cin * p.Cout * 2u + 127u) & ~127u;
-  const uint32_t tail = (2 * kHaloMaxSlices + 4) * 8 + 16 + 8 * p.Cout * 4 + 64;
+  static const int halo3 = [] {
+    const char* e = getenv("B200SEG_HALO3");
+    return (e && e[0] == '0') ? 0 : 1;            // input-slice-major kernel for the 3-D layers (default on)
+  }();
+  const bool use3 = halo3 && p.kd == 3;
+  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + 8 * p.Cout * 4 + 64;
   int ns = (int)((maxsm - 256 - (int)wbytes - (int)tail) / (int)slice);
   if (ns > kHaloMaxSlices) ns = kHaloMaxSlices;
   B200_CHECK_ARG(ns >= p.kd + 1, "conv_halo: slices do not fit in shared memory");
   p.nslices = ns;
   int tc = 32;
-  while (tc < 2 * p.Cout) tc *= 2;
+  while (tc < (use3 ? kAccRing : 2) * p.Cout) tc *= 2;
   p.tmem_cols = tc;
   static const int swap = [] {
     const char* e = getenv("B200SEG_HALO_SWAP");
@@ -470,7 +801,13 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = sms < p.nitems ? sms : p.nitems;
 #define HALO_LAUNCH(CI, CO, K) launch_k(conv_halo_kernel<CI, CO, K>, grid, kHaloThreads, smem_bytes, st, p)
-  if (p.kd == 3) {
+#define HALO3_LAUNCH(CI, CO) launch_k(conv_halo3_kernel<CI, CO>, grid, kHaloThreads, smem_bytes, st, p)
+  if (use3) {
+    if (p.Cin == 16 && p.Cout == 16) HALO3_LAUNCH(16, 16);
+    else if (p.Cin == 16) HALO3_LAUNCH(16, 32);
+    else if (p.Cout == 16) HALO3_LAUNCH(32, 16);
+    else HALO3_LAUNCH(32, 32);
+  } else if (p.kd == 3) {
     if (p.Cin == 16 && p.Cout == 16) HALO_LAUNCH(16, 16, 3);
     else if (p.Cin == 16) HALO_LAUNCH(16, 32, 3);
     else if (p.Cout == 16) HALO_LAUNCH(32, 16, 3);
@@ -482,6 +819,7 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     else HALO_LAUNCH(32, 32, 1);
   }
 #undef HALO_LAUNCH
+#undef HALO3_LAUNCH
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }

@@ -20,10 +20,12 @@ fp32 ``probs`` tensor: the accuracy comes from the loss pass) and put the collec
 Data parallel (``enable_data_parallel()`` active): the loss partial sums are all-reduced between the
 loss pass and its finalize (global-batch-exact Dice), and the flat gradient bucket is SUM-all-reduced in two pieces:
 everything from the deepest encoder block to the head (96 % of the bytes; complete when ~40 % of the backward is
-done) starts its all-reduce right there and overlaps the rest of the backward, the remainder follows at the end.  With
-``B200SEG_NCCL_IN_GRAPH=1`` (default) the NCCL kernels are captured INSIDE the one graph (thread-local capture mode,
-so the NCCL watchdog thread cannot invalidate the capture); if that capture fails the step falls back to three
-graphs with the collectives launched between them.
+done) starts its all-reduce right there and overlaps the rest of the backward, the remainder follows at the end
+(eager mode and the one-graph mode).  By default the collectives stay BETWEEN the graphs of a captured step (forward +
+loss sums | all-reduce | backward | all-reduce | optimizer).  ``B200SEG_NCCL_IN_GRAPH=1`` captures the NCCL kernels
+INSIDE one graph (thread-local capture mode, so the NCCL watchdog thread cannot invalidate the capture): measured on
+2 x B200 it replays correctly and is no faster (3.44 vs 3.43 ms per step), but tearing the process group down while
+such a graph is alive hangs on this stack (torch 2.11 / NCCL 2.28), so it is opt-in.
 """
 from __future__ import annotations
 
@@ -183,7 +185,7 @@ class GraphedStep:
     # ------------------------------------------------------------------ capture
     def _capture(self):
         torch.cuda.synchronize()
-        in_graph = self.dp and os.environ.get("B200SEG_NCCL_IN_GRAPH", "1") != "0"
+        in_graph = self.dp and os.environ.get("B200SEG_NCCL_IN_GRAPH", "0") == "1"
         if not self.dp or in_graph:
             try:
                 g = torch.cuda.CUDAGraph()

@@ -65,6 +65,8 @@ def _worker(rank, world, port, q):
     errs_t = sorted(((p.grad - ref_t[n]).norm() / (ref_t[n].norm() + 1e-12)).item()
                     for n, p in model.named_parameters())
     ngraphs = len(step.graphs)
+    del step
+    torch.cuda.synchronize()
     b200.disable_data_parallel()
     q.put((rank, max(abs(loss.item() - loss_g.item()), abs(loss_s.item() - loss_t.item())),
            max(errs[len(errs) // 2], errs_t[len(errs_t) // 2]), max(errs[-1], errs_t[-1]), ngraphs))
@@ -86,4 +88,4 @@ def test_nccl_two_rank_matches_global_batch():
     for rank, dloss, med, worst, ngraphs in res:
         assert dloss < 1e-5, (rank, dloss)
         assert med < 5e-3 and worst < 5e-2, (rank, med, worst)
-        print(f"rank {rank}: graphs per step = {ngraphs} (1 = NCCL captured inside the step graph)")
+        print(f"rank {rank}: graphs per step = {ngraphs} (collectives between the graphs; 1 = NCCL captured inside)")
