@@ -25,7 +25,7 @@ namespace b200seg {
 
 constexpr int HT_W = 8, HT_H = 16;            // output tile (w, h); M = 128 rows = (hh, ww)
 constexpr int HP_W = HT_W + 2, HP_H = HT_H + 2;
-constexpr int kHaloMaxSlices = 8;
+constexpr int kHaloMaxSlices = 16;
 constexpr int kLoaderWarps = 8;
 constexpr int kHaloThreads = 32 * (1 + 4 + kLoaderWarps);
 constexpr int kMaxPieces = (HP_H * HP_W * 4 + 32 * kLoaderWarps - 1) / (32 * kLoaderWarps);   // Cin <= 32
@@ -48,7 +48,17 @@ struct HaloArgs {
   int tmem_cols;
   int swap_lbo_sbo;       // debug: swap the roles of the two descriptor strides
   int cp_async;           // 1: loaders use cp.async (zfill) + mbarrier completion; 0: register-staged copies
+  int exp;                // debug experiments (B200SEG_HALO_EXP bitmask): 1 no MMAs, 2 no epilogue work, 4 no loads
+  long long* dbg;         // debug timeline (B200SEG_HALO_DBG=1): [role 0..3][64 events] clock64 stamps of CTA 0
 };
+
+__device__ __forceinline__ void halo_stamp(const HaloArgs& p, int role, int idx) {
+  if (p.dbg != nullptr && blockIdx.x == 0 && idx < 64) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[role * 64 + idx] = t;
+  }
+}
 
 __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
@@ -396,14 +406,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
 //   * accumulators: ring of kAccRing slots of Cout columns; slot of output o = (running output count) % ring; an
 //     output is complete when the input slice two further on has been issued (commit -> tfull[slot]);
 //   * all MMAs accumulate (the instruction-wide accumulate flag cannot distinguish the fresh third of its columns):
-//     the epilogue hands a slot back ZEROED (tcgen05.st) and the whole ring is zeroed once at kernel start;
+//     the epilogue reads a slot into registers, hands it back ZEROED (tcgen05.st) at once and only then does its
+//     arithmetic; the whole ring is zeroed once at kernel start.  (Clearing a slot with an extra non-accumulating
+//     zero x zero MMA instead was measured: same time at 16 channels, 13 % slower at 32.)
 //   * at the ends of an item's d-range the column range shrinks to the outputs that exist (N = Cout or 2*Cout,
 //     weight rows offset accordingly), and a range that would wrap around the ring is issued in two pieces;
 //   * the weight image in smem is the packed image permuted at load time to [(kh,kw)][Cin/8][kd reversed][Cout][8].
 // Loaders (cp.async, zero fill = conv padding), slice ring, epilogue arithmetic and statistics are those of
 // conv_halo_kernel above.
 // ------------------------------------------------------------------------------------------------
-constexpr int kAccRing = 8;
+constexpr int kAccRing = 16;
+constexpr int kH3Loaders = 4;          // loader warps of the input-slice-major kernel (warps 9..12)
+constexpr int kH3Pieces = (HP_H * HP_W * 4 + 32 * kH3Loaders - 1) / (32 * kH3Loaders);   // Cin <= 32
+constexpr int kHaloDepth = 6;          // cp.async groups (slices) in flight per loader thread; must be < ring slices
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloArgs p) {
@@ -426,7 +441,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
   uint64_t* tfull = sempty + kHaloMaxSlices;
   uint64_t* tempty = tfull + R;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + R);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][2][Cout]
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [8 epilogue warps][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -437,7 +452,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslices; ++s) {
-      mbar_init(&sfull[s], 32 * kLoaderWarps);   // cp.async loader: one (deferred) arrive per loader thread
+      mbar_init(&sfull[s], 1);                   // ONE arrive: by the loader warp that staged the slice
       mbar_init(&sempty[s], 1);                  // tcgen05.commit
     }
     for (int a = 0; a < R; ++a) {
@@ -457,12 +472,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
     const uint32_t dst = ((t9 * CP + plane) * 3u + (2u - kd)) * COUT + co;
     *reinterpret_cast<uint4*>(s_w + dst * 16u) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + g * 16u);
   }
-  for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) halo_stamp(p, 0, 63);
   if (warp >= 1 && warp <= 4) {
     // the accumulator ring starts at zero (every MMA accumulates)
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -502,14 +518,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
       for (int i = 0; i < nsl; ++i) {
         const uint32_t sl = gs + (uint32_t)i;
         mbar_wait(&sfull[sl % p.nslices], (sl / p.nslices) & 1u);
+        if (lane == 0) halo_stamp(p, 0, (int)sl);
         if (i < nd) {
           // output i is touched for the first time: its slot must have been drained (and zeroed) by the epilogue
           const uint32_t gn_ = go + (uint32_t)i;
           mbar_wait(&tempty[gn_ % R], ((gn_ / R) & 1u) ^ 1u);
         }
-        // slices written by cp.async (generic proxy) must be ordered before the tensor core's async-proxy reads
-        fence_proxy_async();
-        tc_fence_after();
+        // (the loader warp that staged the slice has waited for its cp.async group and executed
+        //  fence.proxy.async BEFORE the arrive: the data is already ordered for the tensor core's async-proxy reads)
+        if (!(p.exp & 8)) tc_fence_after();
         if (elect_one()) {
           const int lo = i - 2 > 0 ? i - 2 : 0;
           const int hi = i < nd - 1 ? i : nd - 1;
@@ -531,42 +548,53 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
               for (int kc = 0; kc < kchunks; ++kc) {
                 const uint32_t a_off = ((uint32_t)(2 * kc) * PLANE + (uint32_t)((t9 / 3) * HP_W + (t9 % 3)) * 16u) >> 4;
                 const uint32_t b_off = ((uint32_t)(t9 * CP + 2 * kc) * 3u * COUT * 16u) >> 4;
-                umma_bf16(tacc, a_base + a_off, b_base + b_off, idesc, 1u);
+                if (!(p.exp & 1)) umma_bf16(tacc, a_base + a_off, b_base + b_off, idesc, 1u);
               }
             o0 += cnt;
           }
           if (i >= 2) umma_commit(&tfull[(go + (uint32_t)(i - 2)) % R]);   // output i-2 has all three contributions
           umma_commit(&sempty[sl % p.nslices]);                            // this input slice is consumed
+          halo_stamp(p, 1, (int)sl);
         }
         __syncwarp();
       }
       gs += (uint32_t)nsl;
       go += (uint32_t)nd;
     }
-  } else if (warp >= 5) {
-    // ===================================================== loaders (8 warps, cp.async, ring-deep prefetch)
-    constexpr int LT = 32 * kLoaderWarps;
-    const int lt = threadIdx.x - 160;
-    const int pieces = HP_H * HP_W * CP;
-    int poff[kMaxPieces], phh[kMaxPieces], pww[kMaxPieces];
-    bool pval[kMaxPieces];
-#pragma unroll
-    for (int j = 0; j < kMaxPieces; ++j) {
-      const int q = lt + j * LT;
-      pval[j] = q < pieces;
-      const int qq = pval[j] ? q : 0;
-      const int v = qq / CP, plane = qq - v * CP;
-      phh[j] = v / HP_W;
-      pww[j] = v - phh[j] * HP_W;
-      poff[j] = plane * (int)PLANE + v * 16;
-      pww[j] |= plane << 16;
-    }
+  } else if (warp >= 9) {
+    // ===================================================== loaders: 4 warps, warp w stages the input slices
+    // sl = w (mod 4) on its own (all pieces of the slice, 16-byte cp.async with zero fill = conv padding), two
+    // cp.async groups in flight per thread, and signals a slice with ONE mbarrier arrive once its group has landed.
+    // The warps run independently of each other: a warp only ever waits for the free slot of ITS next slice, so
+    // eight slices are in flight per CTA without the loaders coupling to the consumer more tightly than the ring.
+    const int lw = warp - 9;
+    constexpr int pieces = HP_H * HP_W * CP;
+    // (item, slice) iterator advanced by kH3Loaders slices at a time
     int it_item = item_begin, it_i = 0, it_nsl = 0, n = 0, h0 = 0, w0 = 0, d0 = 0, nd = 0;
-    if (it_item < item_end) {
-      decode(it_item, n, h0, w0, d0, nd);
-      it_nsl = nd + KD - 1;
-    }
-    uint32_t sl = 0;
+    auto load_item = [&]() {
+      if (it_item < item_end) {
+        decode(it_item, n, h0, w0, d0, nd);
+        it_nsl = nd + KD - 1;
+      }
+    };
+    auto advance = [&](int steps) {
+      it_i += steps;
+      while (it_item < item_end && it_i >= it_nsl) {
+        it_i -= it_nsl;
+        ++it_item;
+        load_item();
+      }
+    };
+    load_item();
+    advance(lw);
+    uint32_t sl = (uint32_t)lw;
+    int pending = 0;
+    uint32_t pend_sl[2] = {0u, 0u};
+    auto signal = [&](uint32_t which) {
+      fence_proxy_async();            // landed cp.async data -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[which % p.nslices]);
+    };
     while (it_item < item_end) {
       const uint32_t slot = sl % p.nslices;
       mbar_wait(&sempty[slot], ((sl / p.nslices) & 1u) ^ 1u);
@@ -574,105 +602,108 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
       const int d = d0 - pd + it_i;
       const bool dok = (unsigned)d < (unsigned)p.D;
       const bf16* src = p.x + (((long long)n * p.D + (dok ? d : 0)) * p.H) * p.W * p.xld;
-#pragma unroll
-      for (int j = 0; j < kMaxPieces; ++j) {
-        if (!pval[j]) continue;
-        const int plane = pww[j] >> 16, ww = pww[j] & 0xffff;
-        const int h = h0 - 1 + phh[j], w = w0 - 1 + ww;
-        const bool ok = dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
-        const bf16* g = ok ? src + ((long long)h * p.W + w) * p.xld + plane * 8 : p.x;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)poff[j]), "l"(g),
-                     "r"(ok ? 16 : 0)
-                     : "memory");
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sfull[slot])) : "memory");
-      ++it_i;
-      if (it_i == it_nsl) {
-        ++it_item;
-        it_i = 0;
-        if (it_item < item_end) {
-          decode(it_item, n, h0, w0, d0, nd);
-          it_nsl = nd + KD - 1;
+      if (!(p.exp & 4)) {
+#pragma unroll 4
+        for (int q = lane; q < pieces; q += 32) {
+          const int v = q / CP, plane = q - v * CP;
+          const int hh = v / HP_W, ww = v - hh * HP_W;
+          const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+          const bool ok = dok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+          const bf16* g = ok ? src + ((long long)h * p.W + w) * p.xld + plane * 8 : p.x;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(plane * (int)PLANE + v * 16)),
+                       "l"(g), "r"(ok ? 16 : 0)
+                       : "memory");
         }
       }
-      ++sl;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (lane == 0) halo_stamp(p, 2, (int)sl);
+      pend_sl[pending & 1] = sl;
+      ++pending;
+      if (pending >= 2) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        signal(pend_sl[pending & 1]);            // the older of the two groups
+      }
+      advance(kH3Loaders);
+      sl += kH3Loaders;
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (pending >= 1) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      signal(pend_sl[(pending - 1) & 1]);
+    }
   } else {
-    // ===================================================== epilogue warps 1..4
+    // ===================================================== epilogue warps 1..8: two groups of four warps, group g
+    // drains the output slices with (running output count) % 2 == g -- the per-slice chain (barrier wait, TMEM
+    // load, zero store, release) is latency bound, two slices in flight hide it behind the MMAs.
+    // GroupNorm statistics: per-thread (= per output row) partial sums in registers over ALL slices of an item, one
+    // butterfly fold over the warp per item (not per slice); bias from shared memory; the zero hand-back of the
+    // accumulator columns is issued right after the read and only waited for before the slot is released.
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int rw = row % HT_W, rh = row / HT_W;
     const int etid = (warp - 1) * 32 + lane;
+    const uint32_t grp = (uint32_t)(warp - 1) >> 2;
     uint32_t go = 0;
     int cur_n = -1;
     auto flush_stats = [&](int n) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (p.stats != nullptr && n >= 0) {
-        for (int i = etid; i < 2 * p.Cout; i += 128) {
+        for (int i = etid; i < 2 * p.Cout; i += 256) {
           const int which = i / p.Cout, c = i - which * p.Cout;
           double t = 0.0;
 #pragma unroll
-          for (int wq = 0; wq < 4; ++wq) {
+          for (int wq = 0; wq < 8; ++wq) {
             t += (double)s_stat[wq * 2 * p.Cout + i];
             s_stat[wq * 2 * p.Cout + i] = 0.f;
           }
           atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     };
+    float bv[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) bv[j] = p.bias != nullptr ? __ldg(p.bias + j) : 0.f;
+    const bool want_stats = p.stats != nullptr;
     for (int item = item_begin; item < item_end; ++item) {
       int n, h0, w0, d0, nd;
       decode(item, n, h0, w0, d0, nd);
       if (n != cur_n) {
-        if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
+        if (cur_n >= 0 && want_stats) flush_stats(cur_n);
         cur_n = n;
       }
       const int oh = h0 + rh, ow = w0 + rw;
       const bool valid = oh < p.H && ow < p.W;
+      float rs[COUT], rq[COUT];
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) rs[j] = rq[j] = 0.f;
       for (int o = 0; o < nd; ++o, ++go) {
+        if ((go & 1u) != grp) continue;
         const long long vox = (((long long)n * p.D + (d0 + o)) * p.H + oh) * p.W + ow;
         const uint32_t as = go % R;
         mbar_wait(&tfull[as], (go / R) & 1u);
         tc_fence_after();
+        if ((etid & 127) == 0) halo_stamp(p, 3, (int)go);
         const uint32_t tacc = tmem_base + as * (uint32_t)COUT + ((uint32_t)(q * 32) << 16);
+        float va[COUT];
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tacc + (uint32_t)c0, va + c0);
+        // the slot is in registers: hand it back at once, zeroed (all MMAs accumulate)
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16_zero(tacc + (uint32_t)c0);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (p.exp & 2) continue;
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 16) {
           float v[16];
-          tmem_ld16(tacc + (uint32_t)c0, v);
-          tmem_st16_zero(tacc + (uint32_t)c0);            // hand the columns back zeroed (all MMAs accumulate)
-          if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
-          }
-          if (p.stats != nullptr) {
-            float s[16], qq[16];
+          for (int j = 0; j < 16; ++j) v[j] = va[c0 + j] + bv[c0 + j];
+          if (want_stats && valid) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              s[j] = valid ? v[j] : 0.f;
-              qq[j] = s[j] * s[j];
-            }
-#pragma unroll
-            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-              const bool up = (lane & off) != 0;
-#pragma unroll
-              for (int j = 0; j < half; ++j) {
-                const float keep_s = up ? s[j + half] : s[j];
-                const float send_s = up ? s[j] : s[j + half];
-                const float keep_q = up ? qq[j + half] : qq[j];
-                const float send_q = up ? qq[j] : qq[j + half];
-                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-                qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-              }
-            }
-            s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
-            qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
-            if ((lane & 1) == 0) {
-              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              float* sw_ = s_stat + q * 2 * p.Cout;      // this warp's private row: no atomics, fixed order
-              sw_[c0 + col] += s[0];
-              sw_[p.Cout + c0 + col] += qq[0];
+              rs[c0 + j] += v[j];
+              rq[c0 + j] = fmaf(v[j], v[j], rq[c0 + j]);
             }
           }
           if (valid) {
@@ -686,20 +717,48 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
             store8(p.y + vox * p.yld + c0, v);
             store8(p.y + vox * p.yld + c0 + 8, v + 8);
           }
-          if (c0 + 16 >= COUT) {
-            // all columns of the slot are read and zeroed: the MMA issuer may start the next output in it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+      }
+      if (want_stats) {
+        // fold the 32 rows of this warp: after the butterfly lane pair (2k, 2k+1) holds column col(k) of the chunk
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          float s[16], qq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s[j] = rs[c0 + j];
+            qq[j] = rq[c0 + j];
+          }
+#pragma unroll
+          for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+              const float keep_s = up ? s[j + half] : s[j];
+              const float send_s = up ? s[j] : s[j + half];
+              const float keep_q = up ? qq[j + half] : qq[j];
+              const float send_q = up ? qq[j] : qq[j + half];
+              s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              qq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+          qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+          if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            float* sw_ = s_stat + (warp - 1) * 2 * p.Cout;   // this warp's private row: no atomics, fixed order
+            sw_[c0 + col] += s[0];
+            sw_[p.Cout + c0 + col] += qq[0];
           }
         }
       }
     }
-    if (p.stats != nullptr && cur_n >= 0) flush_stats(cur_n);
+    if (want_stats && cur_n >= 0) flush_stats(cur_n);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) halo_stamp(p, 1, 63);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -780,10 +839,10 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     return (e && e[0] == '0') ? 0 : 1;            // input-slice-major kernel for the 3-D layers (default on)
   }();
   const bool use3 = halo3 && p.kd == 3;
-  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + 8 * p.Cout * 4 + 64;
+  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + (use3 ? 16 : 8) * p.Cout * 4 + 64;
   int ns = (int)((maxsm - 256 - (int)wbytes - (int)tail) / (int)slice);
   if (ns > kHaloMaxSlices) ns = kHaloMaxSlices;
-  B200_CHECK_ARG(ns >= p.kd + 1, "conv_halo: slices do not fit in shared memory");
+  B200_CHECK_ARG(ns >= p.kd + 1 && (!use3 || ns > kHaloDepth), "conv_halo: slices do not fit in shared memory");
   p.nslices = ns;
   int tc = 32;
   while (tc < (use3 ? kAccRing : 2) * p.Cout) tc *= 2;
@@ -798,6 +857,22 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     return (e && e[0] == 'r') ? 0 : 1;          // "regs" selects the register-staged loader
   }();
   p.cp_async = cpa;
+  static const int exp_bits = [] {
+    const char* e = getenv("B200SEG_HALO_EXP");
+    return e ? atoi(e) : 0;
+  }();
+  p.exp = exp_bits;
+  p.dbg = nullptr;
+  static const int dbg_on = [] {
+    const char* e = getenv("B200SEG_HALO_DBG");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {               // development aid only: allocates and synchronises
+    if (dbg_buf == nullptr) cudaMalloc(&dbg_buf, 4 * 64 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 4 * 64 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = sms < p.nitems ? sms : p.nitems;
 #define HALO_LAUNCH(CI, CO, K) launch_k(conv_halo_kernel<CI, CO, K>, grid, kHaloThreads, smem_bytes, st, p)
@@ -820,6 +895,18 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   }
 #undef HALO_LAUNCH
 #undef HALO3_LAUNCH
+  if (dbg_on && use3) {
+    long long h[4 * 64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[63];
+    fprintf(stderr, "[halo3 dbg] Cin=%d Cout=%d D=%d H=%d W=%d items=%d dchunk=%d ns=%d  end=%lld ns\n", p.Cin, p.Cout, p.D, p.H,
+            p.W, p.nitems, p.dchunk, p.nslices, h[64 + 63] - t0);
+    for (int i = 0; i < 40; ++i)
+      fprintf(stderr, "  sl %2d: load_issued %7lld  mma_sees_full %7lld  mma_issued %7lld | out %2d epi_sees_full %7lld\n", i,
+              h[128 + i] ? h[128 + i] - t0 : -1, h[i] ? h[i] - t0 : -1, h[64 + i] ? h[64 + i] - t0 : -1, i,
+              h[192 + i] ? h[192 + i] - t0 : -1);
+  }
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
