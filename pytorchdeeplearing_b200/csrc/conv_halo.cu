@@ -412,16 +412,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const HaloAr
 //   * at the ends of an item's d-range the column range shrinks to the outputs that exist (N = Cout or 2*Cout,
 //     weight rows offset accordingly), and a range that would wrap around the ring is issued in two pieces;
 //   * the weight image in smem is the packed image permuted at load time to [(kh,kw)][Cin/8][kd reversed][Cout][8].
-// Loaders (cp.async, zero fill = conv padding), slice ring, epilogue arithmetic and statistics are those of
-// conv_halo_kernel above.
+// The per-slice chain of one CTA (barrier waits, MMA issue by a single thread, commits, TMEM read-and-zero) is latency
+// bound (tools/halo_timeline.py: ~460 ns of synchronisation + ~220 ns of MMA issue per slice, tensor pipe 15 % busy),
+// so the kernel is built to run TWO CTAs per SM: 288 threads (1 MMA issuer, 4 epilogue, 4 loader warps), <= 112 KB of
+// shared memory (4-8 slices), 128 / 256 TMEM columns, and the host splits d so that there are ~2 items per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kAccRing = 16;
-constexpr int kH3Loaders = 4;          // loader warps of the input-slice-major kernel (warps 9..12)
-constexpr int kH3Pieces = (HP_H * HP_W * 4 + 32 * kH3Loaders - 1) / (32 * kH3Loaders);   // Cin <= 32
+constexpr int kAccRing = 8;
+constexpr int kH3Loaders = 4;          // loader warps of the input-slice-major kernel (warps 5..8)
+constexpr int kH3Threads = 32 * (1 + 4 + kH3Loaders);   // 288 threads, TWO CTAs per SM
 constexpr int kHaloDepth = 6;          // cp.async groups (slices) in flight per loader thread; must be < ring slices
 
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloArgs p) {
+template <int CIN, int COUT, int NCTA>
+__global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const HaloArgs p) {
   PDL_ENTER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
   uint64_t* tfull = sempty + kHaloMaxSlices;
   uint64_t* tempty = tfull + R;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + R);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [8 epilogue warps][2][Cout]
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -472,7 +474,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
     const uint32_t dst = ((t9 * CP + plane) * 3u + (2u - kd)) * COUT + co;
     *reinterpret_cast<uint4*>(s_w + dst * 16u) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + g * 16u);
   }
-  for (int i = threadIdx.x; i < 16 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
+  float* s_bias = s_stat + 8 * COUT;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -561,15 +565,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
       gs += (uint32_t)nsl;
       go += (uint32_t)nd;
     }
-  } else if (warp >= 9) {
+  } else if (warp >= 5) {
     // ===================================================== loaders: 4 warps, warp w stages the input slices
-    // sl = w (mod 4) on its own (all pieces of the slice, 16-byte cp.async with zero fill = conv padding), two
-    // cp.async groups in flight per thread, and signals a slice with ONE mbarrier arrive once its group has landed.
-    // The warps run independently of each other: a warp only ever waits for the free slot of ITS next slice, so
-    // eight slices are in flight per CTA without the loaders coupling to the consumer more tightly than the ring.
-    const int lw = warp - 9;
+    // sl = w (mod 4) on its own (all pieces of the slice, 16-byte cp.async with zero fill = conv padding), waits
+    // for them to land and signals the slice with ONE mbarrier arrive.  The warps run independently: four slices
+    // are in flight per CTA, eight per SM (two CTAs are resident).
+    const int lw = warp - 5;
     constexpr int pieces = HP_H * HP_W * CP;
-    // (item, slice) iterator advanced by kH3Loaders slices at a time
     int it_item = item_begin, it_i = 0, it_nsl = 0, n = 0, h0 = 0, w0 = 0, d0 = 0, nd = 0;
     auto load_item = [&]() {
       if (it_item < item_end) {
@@ -587,9 +589,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
     };
     load_item();
     advance(lw);
-    uint32_t sl = (uint32_t)lw;
-    int pending = 0;
-    uint32_t pend_sl[2] = {0u, 0u};
+    uint32_t sl = (uint32_t)lw, prev_sl = 0u;
+    bool have_prev = false;
     auto signal = [&](uint32_t which) {
       fence_proxy_async();            // landed cp.async data -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -617,23 +618,28 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (lane == 0) halo_stamp(p, 2, (int)sl);
-      pend_sl[pending & 1] = sl;
-      ++pending;
-      if (pending >= 2) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        signal(pend_sl[pending & 1]);            // the older of the two groups
+      if (NCTA == 2) {
+        // two CTAs per SM, 4-8 slice ring: one slice in flight per warp (eight per SM)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        signal(sl);
+      } else {
+        // one CTA per SM, deep ring: two cp.async groups in flight per warp; signal the older one
+        if (have_prev) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          signal(prev_sl);
+        }
+        prev_sl = sl;
+        have_prev = true;
       }
       advance(kH3Loaders);
       sl += kH3Loaders;
     }
-    if (pending >= 1) {
+    if (NCTA != 2 && have_prev) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      signal(pend_sl[(pending - 1) & 1]);
+      signal(prev_sl);
     }
   } else {
-    // ===================================================== epilogue warps 1..8: two groups of four warps, group g
-    // drains the output slices with (running output count) % 2 == g -- the per-slice chain (barrier wait, TMEM
-    // load, zero store, release) is latency bound, two slices in flight hide it behind the MMAs.
+    // ===================================================== epilogue warps 1..4
     // GroupNorm statistics: per-thread (= per output row) partial sums in registers over ALL slices of an item, one
     // butterfly fold over the warp per item (not per slice); bias from shared memory; the zero hand-back of the
     // accumulator columns is issued right after the read and only waited for before the slot is released.
@@ -641,28 +647,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
     const int row = q * 32 + lane;
     const int rw = row % HT_W, rh = row / HT_W;
     const int etid = (warp - 1) * 32 + lane;
-    const uint32_t grp = (uint32_t)(warp - 1) >> 2;
     uint32_t go = 0;
     int cur_n = -1;
     auto flush_stats = [&](int n) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (p.stats != nullptr && n >= 0) {
-        for (int i = etid; i < 2 * p.Cout; i += 256) {
+        for (int i = etid; i < 2 * p.Cout; i += 128) {
           const int which = i / p.Cout, c = i - which * p.Cout;
           double t = 0.0;
 #pragma unroll
-          for (int wq = 0; wq < 8; ++wq) {
+          for (int wq = 0; wq < 4; ++wq) {
             t += (double)s_stat[wq * 2 * p.Cout + i];
             s_stat[wq * 2 * p.Cout + i] = 0.f;
           }
           atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     };
-    float bv[COUT];
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) bv[j] = p.bias != nullptr ? __ldg(p.bias + j) : 0.f;
     const bool want_stats = p.stats != nullptr;
     for (int item = item_begin; item < item_end; ++item) {
       int n, h0, w0, d0, nd;
@@ -677,28 +679,36 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo3_kernel(const HaloA
 #pragma unroll
       for (int j = 0; j < COUT; ++j) rs[j] = rq[j] = 0.f;
       for (int o = 0; o < nd; ++o, ++go) {
-        if ((go & 1u) != grp) continue;
         const long long vox = (((long long)n * p.D + (d0 + o)) * p.H + oh) * p.W + ow;
         const uint32_t as = go % R;
         mbar_wait(&tfull[as], (go / R) & 1u);
         tc_fence_after();
-        if ((etid & 127) == 0) halo_stamp(p, 3, (int)go);
+        if (etid == 0) halo_stamp(p, 3, (int)go);
         const uint32_t tacc = tmem_base + as * (uint32_t)COUT + ((uint32_t)(q * 32) << 16);
-        float va[COUT];
-#pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tacc + (uint32_t)c0, va + c0);
-        // the slot is in registers: hand it back at once, zeroed (all MMAs accumulate)
-#pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16_zero(tacc + (uint32_t)c0);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-        if (p.exp & 2) continue;
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 16) {
           float v[16];
+          tmem_ld16(tacc + (uint32_t)c0, v);
+          {   // hand the columns back zeroed (all MMAs accumulate); completion is awaited before the release below
+            const uint32_t z = 0u;
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                ::"r"(tacc + (uint32_t)c0), "r"(z)
+                : "memory");
+          }
+          if (c0 + 16 >= COUT) {
+            // every column of the slot is read and its zeroing issued: release it before the arithmetic
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+          }
+          if (p.exp & 2) continue;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = va[c0 + j] + bv[c0 + j];
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
           if (want_stats && valid) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -801,9 +811,10 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     HALO_ATTR(16, 16, 3); HALO_ATTR(16, 32, 3); HALO_ATTR(32, 16, 3); HALO_ATTR(32, 32, 3);
     HALO_ATTR(16, 16, 1); HALO_ATTR(16, 32, 1); HALO_ATTR(32, 16, 1); HALO_ATTR(32, 32, 1);
 #undef HALO_ATTR
-#define HALO3_ATTR(CI, CO) \
-  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm))
-    HALO3_ATTR(16, 16); HALO3_ATTR(16, 32); HALO3_ATTR(32, 16); HALO3_ATTR(32, 32);
+#define HALO3_ATTR(CI, CO, NC) \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm)); \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+    HALO3_ATTR(16, 16, 2); HALO3_ATTR(16, 32, 2); HALO3_ATTR(32, 16, 2); HALO3_ATTR(32, 32, 1);
 #undef HALO3_ATTR
     g_halo_init[device] = 1;
   }
@@ -822,27 +833,33 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.th = (p.H + HT_H - 1) / HT_H;
   const int cols = p.N * p.th * p.tw;
   const int sms = num_sms(device);
-  // split d so that the grid covers the chip (each extra chunk re-loads kd-1 halo slices)
+  static const int halo3 = [] {
+    const char* e = getenv("B200SEG_HALO3");
+    return (e && e[0] == '0') ? 0 : 1;            // input-slice-major kernel for the 3-D layers (default on)
+  }();
+  const bool use3 = halo3 && p.kd == 3;
+  // split d so that the grid covers the chip (each extra chunk re-loads kd-1 halo slices).  The input-slice-major
+  // kernel runs TWO CTAs per SM (and wants two items per SM) whenever six or more slices fit beside the resident
+  // weights in half an SM's shared memory; 32 -> 32 channels (55 KB of weights, 11.5 KB slices) stays at one CTA per SM
+  // with a deep ring (measured: 30.7 us at one CTA, 34.8 us at two, 48^3).
+  const uint32_t slice = (uint32_t)(p.Cin / 8) * HP_H * HP_W * 16u;
+  const uint32_t wbytes = ((uint32_t)(p.kd * 9) * p.Cin * p.Cout * 2u + 127u) & ~127u;
+  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + (use3 ? 9 : 8) * p.Cout * 4 + 64;
+  const bool two = use3 && !(p.Cin == 32 && p.Cout == 32);        // (= six slices fit beside the weights in 112 KB)
+  const int slots = two ? 2 * sms : sms;
   int ndch = 1;
-  if (cols < sms) {
-    ndch = sms / cols;                 // items <= #SM: one item per CTA, no second wave
+  if (cols < slots) {
+    ndch = slots / cols;               // items <= slots: one item per CTA, no second wave
     if (ndch > p.D) ndch = p.D;
     if (ndch < 1) ndch = 1;
   }
   p.dchunk = (p.D + ndch - 1) / ndch;
   p.ndchunks = (p.D + p.dchunk - 1) / p.dchunk;
   p.nitems = cols * p.ndchunks;
-  const uint32_t slice = (uint32_t)(p.Cin / 8) * HP_H * HP_W * 16u;
-  const uint32_t wbytes = ((uint32_t)(p.kd * 9) * p.Cin * p.Cout * 2u + 127u) & ~127u;
-  static const int halo3 = [] {
-    const char* e = getenv("B200SEG_HALO3");
-    return (e && e[0] == '0') ? 0 : 1;            // input-slice-major kernel for the 3-D layers (default on)
-  }();
-  const bool use3 = halo3 && p.kd == 3;
-  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + (use3 ? 16 : 8) * p.Cout * 4 + 64;
-  int ns = (int)((maxsm - 256 - (int)wbytes - (int)tail) / (int)slice);
-  if (ns > kHaloMaxSlices) ns = kHaloMaxSlices;
-  B200_CHECK_ARG(ns >= p.kd + 1 && (!use3 || ns > kHaloDepth), "conv_halo: slices do not fit in shared memory");
+  const int budget = two ? 112 * 1024 : maxsm;
+  int ns = (int)((budget - 256 - (int)wbytes - (int)tail) / (int)slice);
+  if (ns > (two ? 8 : kHaloMaxSlices)) ns = two ? 8 : kHaloMaxSlices;
+  B200_CHECK_ARG(ns >= p.kd + 1, "conv_halo: slices do not fit in shared memory");
   p.nslices = ns;
   int tc = 32;
   while (tc < (use3 ? kAccRing : 2) * p.Cout) tc *= 2;
@@ -874,14 +891,14 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     p.dbg = dbg_buf;
   }
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
-  int grid = sms < p.nitems ? sms : p.nitems;
+  int grid = slots < p.nitems ? slots : p.nitems;
 #define HALO_LAUNCH(CI, CO, K) launch_k(conv_halo_kernel<CI, CO, K>, grid, kHaloThreads, smem_bytes, st, p)
-#define HALO3_LAUNCH(CI, CO) launch_k(conv_halo3_kernel<CI, CO>, grid, kHaloThreads, smem_bytes, st, p)
+#define HALO3_LAUNCH(CI, CO, NC) launch_k(conv_halo3_kernel<CI, CO, NC>, grid, kH3Threads, smem_bytes, st, p)
   if (use3) {
-    if (p.Cin == 16 && p.Cout == 16) HALO3_LAUNCH(16, 16);
-    else if (p.Cin == 16) HALO3_LAUNCH(16, 32);
-    else if (p.Cout == 16) HALO3_LAUNCH(32, 16);
-    else HALO3_LAUNCH(32, 32);
+    if (p.Cin == 16 && p.Cout == 16) HALO3_LAUNCH(16, 16, 2);
+    else if (p.Cin == 16) HALO3_LAUNCH(16, 32, 2);
+    else if (p.Cout == 16) HALO3_LAUNCH(32, 16, 2);
+    else HALO3_LAUNCH(32, 32, 1);
   } else if (p.kd == 3) {
     if (p.Cin == 16 && p.Cout == 16) HALO_LAUNCH(16, 16, 3);
     else if (p.Cin == 16) HALO_LAUNCH(16, 32, 3);
