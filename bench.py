@@ -195,7 +195,7 @@ def _emit(line: dict):
 # per-kernel timing wrapper (instrumentation around the real CudaBackend)
 # ------------------------------------------------------------------------------------------------
 class TimedBackend:
-    TIMED = ("conv", "wgrad", "apply", "gn_bwd_reduce", "gn_bwd_apply", "gn_finalize", "gn_bwd_finalize",
+    TIMED = ("conv", "conv_bwdstats", "wgrad", "apply", "gn_bwd_reduce", "gn_bwd_apply", "gn_finalize", "gn_bwd_finalize",
              "apply_gn", "gn_bwd_reduce_gn", "gn_bwd_apply_gn", "gn_bwd_fused_gn", "pack_weight", "unpack_wgrad",
              "colsum", "head_probs", "head_fwd", "head_bwd", "loss_partials", "loss_finalize", "loss_bwd", "pool_fwd",
              "pool_bwd", "pack_many", "unpack_many", "dropout_masks", "metric_finalize", "adam_step")
@@ -235,6 +235,9 @@ class TimedBackend:
                   and y.numel() // y.shape[-1] >= 65536 and x.shape[-1] * y.shape[-1] <= (512 if kind == 3 else 2048)):
                 path = "/mma.sync-pointwise"      # pw_mma.cu takes these shapes ahead of the tcgen05 kernel
             return f"conv[k{kind}{path}] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
+        if name == "conv_bwdstats":
+            kind, dims, x, wpk, y = a[:5]
+            return f"conv+gn_bwd_sums[k{kind}/tcgen05-halo] {x.shape[-1]}->{y.shape[-1]}@{tuple(y.shape[1:4])}"
         if name == "wgrad":
             kind, dims, x, dy = a[:4]
             return f"wgrad[k{kind}] {x.shape[-1]}x{dy.shape[-1]}@{tuple(dy.shape[1:4])}"
@@ -258,6 +261,12 @@ class TimedBackend:
             else:
                 flops = 2.0 * vox_out * y.shape[-1] * taps_cin
             return nbytes(x) + nbytes(y) + nbytes(w) + nbytes(addend), flops
+        if name == "conv_bwdstats":
+            kind, dims, x, wpk, y, addend, yfwd = a[:7]
+            w = wpk.t if hasattr(wpk, "t") else wpk
+            vox_out = y.numel() // y.shape[-1]
+            return (nbytes(x) + nbytes(y) + nbytes(w) + nbytes(addend) + nbytes(yfwd),
+                    2.0 * vox_out * y.shape[-1] * (w.numel() // y.shape[-1]))
         if name == "wgrad":
             kind, dims, x, dy, dwp = a[:5]
             vox = dy.numel() // dy.shape[-1]

@@ -61,6 +61,7 @@ typedef struct b200seg_tensor {
 } b200seg_tensor;
 
 typedef void* b200seg_stream; /* cudaStream_t */
+struct b200seg_gn;
 
 int b200seg_version(void);
 const char* b200seg_last_error(void);
@@ -109,6 +110,19 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
                  const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device,
                  b200seg_stream stream);
 
+/* Data-gradient convolution that ALSO accumulates the GroupNorm-backward sums of the layer behind its output:
+ * g = conv_kind(x, wpk) [+ addend] is dL/d(activation) of the layer whose raw conv output is `yfwd` and whose
+ * GroupNorm / dropout coefficients follow from `gn` (its forward statistics); with m = [yfwd*A + B > 0]
+ *   sums[n][c][0] += sum g*m,   sums[n][c][1] += sum g*m*yfwd        (double [N][C][3], caller zero-fills; [2] untouched)
+ * i.e. what b200seg_gn_bwd_reduce_gn would compute in a separate pass over g and yfwd (native_group_norm_backward +
+ * threshold_backward, VNet3d.py:9-15).  Follow with b200seg_gn_bwd_apply_gn(..., sum_y_from_stats = 1).  Only the
+ * 3-D halo-staged 16/32-channel 3x3x3 kernel has this epilogue: ask b200seg_conv_bwdstats_supported first. */
+int b200seg_conv_bwdstats_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                                    const b200seg_tensor* addend, const b200seg_tensor* yfwd);
+int b200seg_conv_bwdstats(int kind, int dims, const b200seg_tensor* x, const void* wpk, int w_dtype,
+                          const b200seg_tensor* y, const b200seg_tensor* addend, const b200seg_tensor* yfwd,
+                          const struct b200seg_gn* gn, double* sums, int device, b200seg_stream stream);
+
 /* 1 if b200seg_conv runs (kind, Cin -> Cout) on the tcgen05 + TMA path when given bf16 activations and
  * B200SEG_BF16_TC weights ([tap][Cout][Cin] for the forward form, [tap'][Cin][Cout], taps flipped, for the
  * data-gradient form); 0 -> pack [tap][K][N] and use the CUDA-core path. */
@@ -154,7 +168,8 @@ int b200seg_gn_bwd_reduce_gn(const b200seg_tensor* g, const b200seg_tensor* y, c
 /* dy as b200seg_gn_bwd_apply; additionally dgamma[c] +=, dbeta[c] +=, dbias[c] += (dbias may be NULL; fp32 atomics
  * over the samples: the caller zero-fills the gradient bucket) */
 int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, const double* sums,
-                            const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int device,
+                            const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias,
+                            int sum_y_from_stats /* 1: sums[..][2] is not filled, sum y = gn->stats[..][0] */, int device,
                             b200seg_stream stream);
 
 /* b200seg_gn_bwd_reduce_gn + b200seg_gn_bwd_apply_gn in ONE launch for small tensors (the 24^3 level and below: the

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "b200seg_unpack_wgrads_multi": ([_vp, _i, _i, _i, _vp], C.c_int),
     "b200seg_upload_table": ([_vp, _i64, _vp, _i, _vp], C.c_int),
     "b200seg_conv": ([_i, _i, _PT, _vp, _i, _vp, _PT, _vp, _PT, _i, _vp], C.c_int),
+    "b200seg_conv_bwdstats_supported": ([_i, _i, _PT, _i, _PT, _PT, _PT], C.c_int),
+    "b200seg_conv_bwdstats": ([_i, _i, _PT, _vp, _i, _PT, _PT, _PT, _PG, _vp, _i, _vp], C.c_int),
     "b200seg_conv_tc_eligible": ([_i, _i, _i], C.c_int),
     "b200seg_conv_halo_eligible": ([_i, _i, _i], C.c_int),
     "b200seg_conv_halo_ws_ntile": ([_i, _i, _i], C.c_int),
@@ -59,7 +61,7 @@ _SIGNATURES = {
     "b200seg_apply": ([_PT, _vp, _PT, _vp, _PT, _PT, _i, _vp], C.c_int),
     "b200seg_apply_gn": ([_PT, _PG, _PT, _PG, _PT, _PT, _i, _vp], C.c_int),
     "b200seg_gn_bwd_reduce_gn": ([_PT, _PT, _PG, _vp, _i, _vp], C.c_int),
-    "b200seg_gn_bwd_apply_gn": ([_PT, _PT, _PG, _vp, _PT, _vp, _vp, _vp, _i, _vp], C.c_int),
+    "b200seg_gn_bwd_apply_gn": ([_PT, _PT, _PG, _vp, _PT, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
     "b200seg_gn_bwd_fused_supported": ([_PT, _PT, _PT, _i], C.c_int),
     "b200seg_gn_bwd_fused_gn": ([_PT, _PT, _PG, _vp, _vp, _PT, _vp, _vp, _vp, _i, _vp], C.c_int),
     "b200seg_gn_bwd_reduce": ([_PT, _PT, _vp, _vp, _i, _vp], C.c_int),
@@ -324,6 +326,24 @@ class CudaBackend:
         self._check(self.lib.b200seg_conv(kind, dims, C.byref(dx), wpk.t.data_ptr(), wpk.code, _p(bias), C.byref(dy),
                                           _p(stats), _ref(da), dev, st))
 
+    fused_bwd_stats = os.environ.get("B200SEG_FUSED_BWD_STATS", "1") != "0"
+
+    def conv_bwdstats_ok(self, kind, dims, x, wpk, y, addend, yfwd):
+        """can ``conv_bwdstats`` take this data-gradient convolution (3-D halo-staged 16/32-channel 3x3x3 layers)?"""
+        if not self.fused_bwd_stats or wpk.code != BF16_HALO or x.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
+            return False
+        dx, dy, da, df = _desc(x), _desc(y), _desc(addend), _desc(yfwd)
+        return bool(self.lib.b200seg_conv_bwdstats_supported(kind, dims, C.byref(dx), wpk.code, C.byref(dy), _ref(da),
+                                                             C.byref(df)))
+
+    def conv_bwdstats(self, kind, dims, x, wpk, y, addend, yfwd, gn, sums):
+        """y = conv(x, wpk) [+ addend] AND sums[n][c][0:2] += {g*m, g*m*yfwd} of the layer (yfwd, gn) whose activation
+        gradient y is: the GroupNorm-backward reduce pass folded into the data-gradient epilogue"""
+        dev, st = self._ds(x)
+        dx, dy, da, df, gg = _desc(x), _desc(y), _desc(addend), _desc(yfwd), self._gn(gn)
+        self._check(self.lib.b200seg_conv_bwdstats(kind, dims, C.byref(dx), wpk.t.data_ptr(), wpk.code, C.byref(dy),
+                                                   _ref(da), C.byref(df), C.byref(gg), sums.data_ptr(), dev, st))
+
     def wgrad(self, kind, dims, a, b, dwp):
         dev, st = self._ds(a)
         da, db = _desc(a), _desc(b)
@@ -363,12 +383,12 @@ class CudaBackend:
         dg, dy, gg = _desc(g), _desc(y), self._gn(gn)
         self._check(self.lib.b200seg_gn_bwd_reduce_gn(C.byref(dg), C.byref(dy), C.byref(gg), sums.data_ptr(), dev, st))
 
-    def gn_bwd_apply_gn(self, g, y, gn, sums, dy, dgamma, dbeta, dbias):
+    def gn_bwd_apply_gn(self, g, y, gn, sums, dy, dgamma, dbeta, dbias, sum_y_from_stats=False):
         dev, st = self._ds(y)
         dg, dyy, dd, gg = _desc(g), _desc(y), _desc(dy), self._gn(gn)
         self._check(self.lib.b200seg_gn_bwd_apply_gn(C.byref(dg), C.byref(dyy), C.byref(gg), sums.data_ptr(),
                                                      C.byref(dd), dgamma.data_ptr(), dbeta.data_ptr(), _p(dbias),
-                                                     dev, st))
+                                                     1 if sum_y_from_stats else 0, dev, st))
 
     fused_gn_bwd = os.environ.get("B200SEG_FUSED_GN_BWD", "1") != "0"
 

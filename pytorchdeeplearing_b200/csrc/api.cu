@@ -28,7 +28,9 @@ int conv_halo_channels_ok(int kind, int cin, int cout);
 int conv_halo_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
                         const b200seg_tensor* addend);
 int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
-              double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
+              double* stats, const b200seg_tensor* addend, int device, cudaStream_t st,
+              const b200seg_tensor* yfwd = nullptr, const b200seg_gn* gn = nullptr, double* sums = nullptr);
+int conv_halo_bwdstats_ok(int dims);
 int pw_mma_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
                      const b200seg_tensor* addend);
 int pw_mma_conv(int kind, int dims, const b200seg_tensor* x, const void* w, const float* bias,
@@ -93,7 +95,7 @@ int ew_gn_bwd_fused(const b200seg_tensor* g, const b200seg_tensor* y, const b200
                     int device, cudaStream_t s);
 int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
                     const b200seg_gn* gn, const double* sums, float* dgamma, float* dbeta, float* dbias,
-                    const b200seg_tensor* dy, int device, cudaStream_t s);
+                    const b200seg_tensor* dy, int device, cudaStream_t s, int sum_y_from_stats = 0);
 int ew_colsum(const b200seg_tensor* dy, float* out, int device, cudaStream_t s);
 int ew_pool_fwd(const b200seg_tensor* x, const b200seg_tensor* out, int dims, int device, cudaStream_t s);
 int ew_pool_bwd(const b200seg_tensor* x, const b200seg_tensor* go, const b200seg_tensor* addend,
@@ -215,6 +217,40 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
   return conv_generic(kind, dims, x, wpk, w_dtype, bias, y, stats, addend, ST(stream));
 }
 
+int b200seg_conv_bwdstats_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                                    const b200seg_tensor* addend, const b200seg_tensor* yfwd) {
+  if (x == nullptr || y == nullptr || yfwd == nullptr) return 0;
+  if (!conv_halo_bwdstats_ok(dims) || !conv_halo_supported(kind, dims, x, w_dtype, y, addend)) return 0;
+  // measured on B200 (VNet3d 96^3 step): with 32 output channels the fused form beats conv + reduce (42 vs 33.5 + 19.5 us
+  // at 48^3); with 16 it loses (125 vs 60 + 34 us at 96^3: the two-CTA kernel has no registers to spare and the layer
+  // is traffic bound once it also reads the producer's raw output).  B200SEG_BWDSTATS_ALL=1 lifts the restriction.
+  static const bool all = [] {
+    const char* e = getenv("B200SEG_BWDSTATS_ALL");
+    return e && e[0] == '1';
+  }();
+  if (y->c != 32 && !all) return 0;
+  if (pw_mma_supported(kind, dims, x, w_dtype, y, addend) || conv_tc_supported(kind, dims, x, w_dtype, y, addend)) return 0;
+  return (yfwd->n == y->n && yfwd->d == y->d && yfwd->h == y->h && yfwd->w == y->w && yfwd->c == y->c &&
+          yfwd->dtype == B200SEG_BF16 && (yfwd->ld % 8) == 0 && (reinterpret_cast<uintptr_t>(yfwd->ptr) % 16) == 0)
+             ? 1 : 0;
+}
+
+int b200seg_conv_bwdstats(int kind, int dims, const b200seg_tensor* x, const void* wpk, int w_dtype,
+                          const b200seg_tensor* y, const b200seg_tensor* addend, const b200seg_tensor* yfwd,
+                          const b200seg_gn* gn, double* sums, int device, b200seg_stream stream) {
+  REQ_TENSOR(x, "x");
+  REQ_TENSOR(y, "y");
+  REQ_TENSOR(yfwd, "yfwd");
+  OPT_TENSOR(addend, "addend");
+  B200_CHECK_ARG(wpk != nullptr && gn != nullptr && sums != nullptr && gn->stats && gn->gamma && gn->beta,
+                 "b200seg_conv_bwdstats: null argument");
+  B200_CHECK_ARG(b200seg_conv_bwdstats_supported(kind, dims, x, w_dtype, y, addend, yfwd),
+                 "b200seg_conv_bwdstats: unsupported shape (query b200seg_conv_bwdstats_supported first)");
+  B200_DEVICE(device);
+  if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
+  return conv_halo(kind, dims, x, wpk, nullptr, y, nullptr, addend, device, ST(stream), yfwd, gn, sums);
+}
+
 int b200seg_conv_tc_eligible(int kind, int cin, int cout) { return conv_tc_channels_ok(kind, cin, cout); }
 
 int b200seg_conv_halo_eligible(int kind, int cin, int cout) { return conv_halo_channels_ok(kind, cin, cout); }
@@ -295,14 +331,15 @@ int b200seg_gn_bwd_reduce_gn(const b200seg_tensor* g, const b200seg_tensor* y, c
 }
 
 int b200seg_gn_bwd_apply_gn(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_gn* gn, const double* sums,
-                            const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int device,
-                            b200seg_stream stream) {
+                            const b200seg_tensor* dy, float* dgamma, float* dbeta, float* dbias, int sum_y_from_stats,
+                            int device, b200seg_stream stream) {
   REQ_TENSOR(g, "g");
   REQ_TENSOR(y, "y");
   REQ_TENSOR(dy, "dy");
   B200_CHECK_ARG(valid_gn(gn, y->c) && sums && dgamma && dbeta, "b200seg_gn_bwd_apply_gn: bad argument");
   B200_DEVICE(device);
-  return ew_gn_bwd_apply(g, y, nullptr, nullptr, gn, sums, dgamma, dbeta, dbias, dy, device, ST(stream));
+  return ew_gn_bwd_apply(g, y, nullptr, nullptr, gn, sums, dgamma, dbeta, dbias, dy, device, ST(stream),
+                         sum_y_from_stats);
 }
 
 int b200seg_gn_bwd_fused_supported(const b200seg_tensor* g, const b200seg_tensor* y, const b200seg_tensor* dy,

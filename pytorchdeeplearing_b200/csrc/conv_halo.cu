@@ -48,6 +48,19 @@ struct HaloArgs {
   int tmem_cols;
   int swap_lbo_sbo;       // debug: swap the roles of the two descriptor strides
   int cp_async;           // 1: loaders use cp.async (zfill) + mbarrier completion; 0: register-staged copies
+  // GroupNorm-backward sums fused into the data-gradient epilogue (b200seg_conv_bwdstats): the output of this conv is
+  // g = dL/d(act) of the layer whose raw output is yfwd; with m = [yfwd*A + B > 0] (A, B = that layer's GroupNorm /
+  // dropout coefficients, derived here from its statistics exactly as gn_cta_coefs does) the epilogue accumulates
+  // sums[n][c][0] += g*m, sums[n][c][1] += g*m*yfwd  (stride 3: [2] = sum yfwd is taken from the forward statistics).
+  const bf16* yfwd;       // nullptr: forward statistics mode (stats = [N][Cout][2])
+  long long yfld;
+  const double* gstats;   // [N][Cout][2] forward statistics of the layer being differentiated
+  const float* ggamma;
+  const float* gbeta;
+  const float* gscale;    // [N][Cout] dropout scale or nullptr
+  int ggroups;
+  double gm;              // elements per group
+  float geps;
   int exp;                // debug experiments (B200SEG_HALO_EXP bitmask): 1 no MMAs, 2 no epilogue work, 4 no loads
   long long* dbg;         // debug timeline (B200SEG_HALO_DBG=1): [role 0..3][64 events] clock64 stamps of CTA 0
 };
@@ -422,7 +435,7 @@ constexpr int kH3Loaders = 4;          // loader warps of the input-slice-major 
 constexpr int kH3Threads = 32 * (1 + 4 + kH3Loaders);   // 288 threads, TWO CTAs per SM
 constexpr int kHaloDepth = 6;          // cp.async groups (slices) in flight per loader thread; must be < ring slices
 
-template <int CIN, int COUT, int NCTA>
+template <int CIN, int COUT, int NCTA, bool BWD>
 __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const HaloArgs p) {
   PDL_ENTER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -477,6 +490,8 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
   for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
   float* s_bias = s_stat + 8 * COUT;
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+  float* s_ab = s_bias + COUT;                                       // [2][Cout]: A, B of the sample being processed
+  double* s_gd = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_ab + 2 * COUT) + 7) & ~(uintptr_t)7);   // [2][Cout] + [8][2]
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -649,6 +664,8 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
     const int etid = (warp - 1) * 32 + lane;
     uint32_t go = 0;
     int cur_n = -1;
+    constexpr bool bwd = BWD;                 // backward-sums epilogue (b200seg_conv_bwdstats): its own instantiation,
+    constexpr int sstride = BWD ? 3 : 2;      // so the plain kernel does not carry its registers
     auto flush_stats = [&](int n) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (p.stats != nullptr && n >= 0) {
@@ -660,8 +677,41 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
             t += (double)s_stat[wq * 2 * p.Cout + i];
             s_stat[wq * 2 * p.Cout + i] = 0.f;
           }
-          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * sstride + which, t);
         }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    // A, B of sample n for the ReLU mask of the backward sums: the same expressions, in the same precision, as
+    // gn_cta_coefs (elementwise.cu), so the mask here equals the one gn_bwd_apply derives later
+    auto load_coefs = [&](int n) {
+      const int cpg = COUT / p.ggroups;
+      if (etid < COUT) {
+        const double* q_ = p.gstats + ((long long)n * COUT + etid) * 2;
+        s_gd[etid] = q_[0];
+        s_gd[COUT + etid] = q_[1];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (etid < p.ggroups) {
+        double sm = 0.0, sq = 0.0;
+        for (int k_ = 0; k_ < cpg; ++k_) {
+          sm += s_gd[etid * cpg + k_];
+          sq += s_gd[COUT + etid * cpg + k_];
+        }
+        const double mean = sm / p.gm;
+        double var = sq / p.gm - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_gd[2 * COUT + etid * 2 + 0] = mean;
+        s_gd[2 * COUT + etid * 2 + 1] = rsqrt(var + (double)p.geps);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (etid < COUT) {
+        const int g_ = etid / cpg;
+        const double mean = s_gd[2 * COUT + g_ * 2 + 0], rstd = s_gd[2 * COUT + g_ * 2 + 1];
+        const double sc = p.gscale ? (double)p.gscale[(long long)n * COUT + etid] : 1.0;
+        const double ga = (double)p.ggamma[etid], be = (double)p.gbeta[etid];
+        s_ab[etid] = (float)(rstd * ga * sc);
+        s_ab[COUT + etid] = (float)((be - mean * rstd * ga) * sc);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -672,6 +722,7 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
       if (n != cur_n) {
         if (cur_n >= 0 && want_stats) flush_stats(cur_n);
         cur_n = n;
+        if (bwd) load_coefs(n);
       }
       const int oh = h0 + rh, ow = w0 + rw;
       const bool valid = oh < p.H && ow < p.W;
@@ -680,6 +731,26 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
       for (int j = 0; j < COUT; ++j) rs[j] = rq[j] = 0.f;
       for (int o = 0; o < nd; ++o, ++go) {
         const long long vox = (((long long)n * p.D + (d0 + o)) * p.H + oh) * p.W + ow;
+        // backward-sums form: the epilogue's global operands (residual addend, the producer's raw output) are requested
+        // BEFORE waiting for the accumulator
+        uint4 adv[BWD ? COUT / 8 : 1], yfv[BWD ? COUT / 8 : 1];
+        if constexpr (BWD) {
+#pragma unroll
+          for (int k_ = 0; k_ < COUT / 8; ++k_) {
+            adv[k_] = make_uint4(0u, 0u, 0u, 0u);
+            yfv[k_] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (valid) {
+            if (p.addend != nullptr) {
+#pragma unroll
+              for (int k_ = 0; k_ < COUT / 8; ++k_)
+                adv[k_] = *reinterpret_cast<const uint4*>(p.addend + vox * p.ald + 8 * k_);
+            }
+#pragma unroll
+            for (int k_ = 0; k_ < COUT / 8; ++k_)
+              yfv[k_] = *reinterpret_cast<const uint4*>(p.yfwd + vox * p.yfld + 8 * k_);
+          }
+        }
         const uint32_t as = go % R;
         mbar_wait(&tfull[as], (go / R) & 1u);
         tc_fence_after();
@@ -709,7 +780,7 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
-          if (want_stats && valid) {
+          if (want_stats && valid && !bwd) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               rs[c0 + j] += v[j];
@@ -718,14 +789,58 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
           }
           if (valid) {
             if (p.addend != nullptr) {
-              float r[16];
-              load8(p.addend + vox * p.ald + c0, r);
-              load8(p.addend + vox * p.ald + c0 + 8, r + 8);
+              if constexpr (BWD) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += r[j];
+                for (int h_ = 0; h_ < 2; ++h_) {
+                  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&adv[c0 / 8 + h_]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(a2[j]);
+                    v[8 * h_ + 2 * j] += f.x;
+                    v[8 * h_ + 2 * j + 1] += f.y;
+                  }
+                }
+              } else {
+                float r[16];
+                load8(p.addend + vox * p.ald + c0, r);
+                load8(p.addend + vox * p.ald + c0 + 8, r + 8);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += r[j];
+              }
             }
-            store8(p.y + vox * p.yld + c0, v);
-            store8(p.y + vox * p.yld + c0 + 8, v + 8);
+            if constexpr (!BWD) {
+              store8(p.y + vox * p.yld + c0, v);
+              store8(p.y + vox * p.yld + c0 + 8, v + 8);
+            } else {
+              // round g to bf16 once: the packed values are what is stored AND what the sums see (a separate reduce
+              // pass would read the stored tensor); coefficients come as 128-bit shared-memory loads
+#pragma unroll
+              for (int h_ = 0; h_ < 2; ++h_) {
+                uint4 pk;
+                __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g2[j] = __floats2bfloat162_rn(v[8 * h_ + 2 * j], v[8 * h_ + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(p.y + vox * p.yld + c0 + 8 * h_) = pk;
+                const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yfv[c0 / 8 + h_]);
+                const int cb = c0 + 8 * h_;
+                const float4 a0 = *reinterpret_cast<const float4*>(s_ab + cb), a1 = *reinterpret_cast<const float4*>(s_ab + cb + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(s_ab + COUT + cb);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_ab + COUT + cb + 4);
+                const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 yy = __bfloat1622float2(y2[j]);
+                  const float2 gg = __bfloat1622float2(g2[j]);
+                  const float d0_ = fmaf(yy.x, aa[2 * j], bb[2 * j]) > 0.f ? gg.x : 0.f;
+                  const float d1_ = fmaf(yy.y, aa[2 * j + 1], bb[2 * j + 1]) > 0.f ? gg.y : 0.f;
+                  rs[cb + 2 * j] += d0_;
+                  rs[cb + 2 * j + 1] += d1_;
+                  rq[cb + 2 * j] = fmaf(d0_, yy.x, rq[cb + 2 * j]);
+                  rq[cb + 2 * j + 1] = fmaf(d1_, yy.y, rq[cb + 2 * j + 1]);
+                }
+              }
+            }
           }
         }
       }
@@ -801,8 +916,18 @@ int conv_halo_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype
 
 static int g_halo_init[64] = {0};
 
+// 1 if conv_halo can fuse the GroupNorm-backward sums of the layer behind `y` into its epilogue (3-D layers only)
+int conv_halo_bwdstats_ok(int dims) {
+  static const int halo3 = [] {
+    const char* e = getenv("B200SEG_HALO3");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return halo3 && dims == 3;
+}
+
 int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias, const b200seg_tensor* y,
-              double* stats, const b200seg_tensor* addend, int device, cudaStream_t st) {
+              double* stats, const b200seg_tensor* addend, int device, cudaStream_t st, const b200seg_tensor* yfwd,
+              const b200seg_gn* gn, double* sums) {
   (void)kind;
   const int maxsm = tc_max_smem(device);
   if (device >= 0 && device < 64 && !g_halo_init[device]) {
@@ -812,9 +937,11 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
     HALO_ATTR(16, 16, 1); HALO_ATTR(16, 32, 1); HALO_ATTR(32, 16, 1); HALO_ATTR(32, 32, 1);
 #undef HALO_ATTR
 #define HALO3_ATTR(CI, CO, NC) \
-  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm)); \
-  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
-    HALO3_ATTR(16, 16, 2); HALO3_ATTR(16, 32, 2); HALO3_ATTR(32, 16, 2); HALO3_ATTR(32, 32, 1);
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm)); \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm)); \
+  B200_CUDA(cudaFuncSetAttribute(conv_halo3_kernel<CI, CO, NC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+    HALO3_ATTR(16, 16, 2); HALO3_ATTR(16, 32, 1); HALO3_ATTR(32, 16, 2); HALO3_ATTR(32, 32, 1);
 #undef HALO3_ATTR
     g_halo_init[device] = 1;
   }
@@ -829,6 +956,22 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   p.N = x->n; p.D = x->d; p.H = x->h; p.W = x->w;
   p.Cin = x->c; p.Cout = y->c;
   p.kd = dims == 3 ? 3 : 1;
+  p.yfwd = nullptr; p.yfld = 0; p.gstats = nullptr; p.ggamma = nullptr; p.gbeta = nullptr; p.gscale = nullptr;
+  p.ggroups = 1; p.gm = 1.0; p.geps = 0.f;
+  if (yfwd != nullptr) {
+    B200_CHECK_ARG(conv_halo_bwdstats_ok(dims) && gn != nullptr && sums != nullptr && stats == nullptr,
+                   "conv_halo: backward statistics need the 3-D input-slice-major kernel");
+    B200_CHECK_ARG(same_geom(yfwd, y) && yfwd->dtype == B200SEG_BF16 && (yfwd->ld % 8) == 0 && al16h(yfwd->ptr) &&
+                       gn->groups > 0 && (y->c % gn->groups) == 0 && gn->groups <= 8,
+                   "conv_halo: bad forward tensor / GroupNorm reference for the backward statistics");
+    p.yfwd = static_cast<const bf16*>(yfwd->ptr);
+    p.yfld = yfwd->ld;
+    p.gstats = gn->stats; p.ggamma = gn->gamma; p.gbeta = gn->beta; p.gscale = gn->scale;
+    p.ggroups = gn->groups;
+    p.gm = (double)(y->c / gn->groups) * (double)gn->vox;
+    p.geps = gn->eps;
+    p.stats = sums;
+  }
   p.tw = (p.W + HT_W - 1) / HT_W;
   p.th = (p.H + HT_H - 1) / HT_H;
   const int cols = p.N * p.th * p.tw;
@@ -839,13 +982,13 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   }();
   const bool use3 = halo3 && p.kd == 3;
   // split d so that the grid covers the chip (each extra chunk re-loads kd-1 halo slices).  The input-slice-major
-  // kernel runs TWO CTAs per SM (and wants two items per SM) whenever six or more slices fit beside the resident
-  // weights in half an SM's shared memory; 32 -> 32 channels (55 KB of weights, 11.5 KB slices) stays at one CTA per SM
-  // with a deep ring (measured: 30.7 us at one CTA, 34.8 us at two, 48^3).
+  // kernel runs TWO CTAs per SM (and wants two items per SM) for 16 output channels; with 32 output channels the
+  // epilogue's register statistics do not fit the 96-register budget of two CTAs (and 32 -> 32 has 55 KB of weights):
+  // one CTA per SM with a deep ring (measured at 32 -> 32 @48^3: 30.7 us at one CTA, 34.8 us at two).
   const uint32_t slice = (uint32_t)(p.Cin / 8) * HP_H * HP_W * 16u;
   const uint32_t wbytes = ((uint32_t)(p.kd * 9) * p.Cin * p.Cout * 2u + 127u) & ~127u;
-  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + (use3 ? 9 : 8) * p.Cout * 4 + 64;
-  const bool two = use3 && !(p.Cin == 32 && p.Cout == 32);        // (= six slices fit beside the weights in 112 KB)
+  const uint32_t tail = (2 * kHaloMaxSlices + (use3 ? 2 * kAccRing : 4)) * 8 + 16 + (use3 ? 11 : 8) * p.Cout * 4 + 64 + (use3 ? (2 * p.Cout + 16) * 8 + 8 : 0);
+  const bool two = use3 && p.Cout == 16;       // 32 output channels: the epilogue's per-thread statistics need > 96 registers
   const int slots = two ? 2 * sms : sms;
   int ndch = 1;
   if (cols < slots) {
@@ -893,10 +1036,14 @@ int conv_halo(int kind, int dims, const b200seg_tensor* x, const void* wpk, cons
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   int grid = slots < p.nitems ? slots : p.nitems;
 #define HALO_LAUNCH(CI, CO, K) launch_k(conv_halo_kernel<CI, CO, K>, grid, kHaloThreads, smem_bytes, st, p)
-#define HALO3_LAUNCH(CI, CO, NC) launch_k(conv_halo3_kernel<CI, CO, NC>, grid, kH3Threads, smem_bytes, st, p)
+#define HALO3_LAUNCH(CI, CO, NC)                                                                         \
+  do {                                                                                                   \
+    if (p.yfwd != nullptr) launch_k(conv_halo3_kernel<CI, CO, NC, true>, grid, kH3Threads, smem_bytes, st, p);  \
+    else launch_k(conv_halo3_kernel<CI, CO, NC, false>, grid, kH3Threads, smem_bytes, st, p);            \
+  } while (0)
   if (use3) {
     if (p.Cin == 16 && p.Cout == 16) HALO3_LAUNCH(16, 16, 2);
-    else if (p.Cin == 16) HALO3_LAUNCH(16, 32, 2);
+    else if (p.Cin == 16) HALO3_LAUNCH(16, 32, 1);
     else if (p.Cout == 16) HALO3_LAUNCH(32, 16, 2);
     else HALO3_LAUNCH(32, 32, 1);
   } else if (p.kd == 3) {

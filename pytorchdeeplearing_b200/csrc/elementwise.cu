@@ -296,6 +296,7 @@ struct GnRef {
   int groups;
   double m;                // elements per group = (C/groups) * voxels
   float eps;
+  int sum_y_from_stats;    // backward: sum of y per (n,c) = stats[n][c][0] (the backward sums came from a conv epilogue)
 };
 
 template <int VEC>
@@ -765,7 +766,8 @@ __device__ __forceinline__ void param_grads_of_sample(const GnRef& gn, const dou
     const double mu = grp[g * 4 + 0], rs = grp[g * 4 + 1], m1 = grp[g * 4 + 2], m2 = grp[g * 4 + 3];
     const double sc = (double)s_f[c], ga = (double)s_f[C + c];
     const double* sp = sums + ((long long)n * C + c) * 3;
-    const double s1 = sp[0] * sc, s2 = sp[1] * sc, s3 = sp[2];
+    const double s1 = sp[0] * sc, s2 = sp[1] * sc;
+    const double s3 = gn.sum_y_from_stats ? gn.stats[((long long)n * C + c) * 2] : sp[2];
     const double qd = -rs * rs * m2, rd = -rs * m1 + rs * rs * mu * m2;
     atomicAdd(dbeta + c, (float)s1);
     atomicAdd(dgamma + c, (float)(rs * (s2 - mu * s1)));
@@ -1174,11 +1176,13 @@ static GnRef make_gnref(const b200seg_gn* g, int C) {
   GnRef r;
   if (g == nullptr || g->stats == nullptr) {
     r.stats = nullptr; r.gamma = nullptr; r.beta = nullptr; r.scale = nullptr; r.groups = 1; r.m = 1.0; r.eps = 0.f;
+    r.sum_y_from_stats = 0;
     return r;
   }
   r.stats = g->stats; r.gamma = g->gamma; r.beta = g->beta; r.scale = g->scale; r.groups = g->groups;
   r.m = (double)(C / g->groups) * (double)g->vox;
   r.eps = g->eps;
+  r.sum_y_from_stats = 0;
   return r;
 }
 
@@ -1242,7 +1246,7 @@ int ew_gn_bwd_finalize(const double* sums, const float* mr, const float* gamma, 
 
 int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const float* coef, const float* coef3,
                     const b200seg_gn* gn, const double* sums, float* dgamma, float* dbeta, float* dbias,
-                    const b200seg_tensor* dy, int device, cudaStream_t s) {
+                    const b200seg_tensor* dy, int device, cudaStream_t s, int sum_y_from_stats) {
   B200_CHECK_ARG(same_geom(g, y) && same_geom(dy, y) && g->dtype == y->dtype && dy->dtype == y->dtype,
                  "gn_bwd_apply: tensor mismatch");
   const bool vok = vec_ok(g) && vec_ok(y) && vec_ok(dy);
@@ -1254,9 +1258,11 @@ int ew_gn_bwd_apply(const b200seg_tensor* g, const b200seg_tensor* y, const floa
     dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
     const int groups = (gn && gn->stats) ? gn->groups : 1;
     const size_t smem = (gn && gn->stats) ? gn_cta_doubles(C, groups, true) * sizeof(double) + (size_t)8 * C * sizeof(float) : 0;
+    GnRef gref = make_gnref(gn, C);
+    gref.sum_y_from_stats = sum_y_from_stats;
     launch_k(gn_bwd_apply_kernel<T, VEC>, grid, 256, smem, s, static_cast<const T*>(g->ptr), g->ld,
                                                      static_cast<const T*>(y->ptr), y->ld, coef, coef3,
-                                                     static_cast<T*>(dy->ptr), dy->ld, C, V, make_gnref(gn, C), sums,
+                                                     static_cast<T*>(dy->ptr), dy->ld, C, V, gref, sums,
                                                      y->n, dgamma, dbeta, dbias);
   });
   B200_LAUNCH_CHECK();

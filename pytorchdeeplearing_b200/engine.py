@@ -48,6 +48,7 @@ class Layer:
     mr: Tensor = None               # (N,G,2)   fp32  mean, rstd    (unfused path only)
     gn: tuple = None                # (stats, gamma, beta, scale, vox, groups, eps): fused-coefficient path
     scale: Optional[Tensor] = None  # (N,Cout) dropout scale or None
+    pre_sums: Optional[Tensor] = None   # backward sums already accumulated by the epilogue of the conv that produced g
 
 
 def _taps(kind: int, dims: int) -> int:
@@ -265,10 +266,13 @@ class Engine:
         return self.grads[name]
 
     def bwd_layer(self, L: Layer, g_act: Tensor, need_dx: bool, dx_out: Optional[Tensor] = None,
-                  dx_addend: Optional[Tensor] = None) -> Optional[Tensor]:
+                  dx_addend: Optional[Tensor] = None, prev: Optional[Layer] = None) -> Optional[Tensor]:
         """Backward of one conv(+GN/drop/ReLU) application.  ``g_act`` is the gradient w.r.t.
         the layer's activation output (or w.r.t. the raw conv output when the layer has no
-        GroupNorm).  Returns the gradient w.r.t. the layer input (written to ``dx_out``)."""
+        GroupNorm).  Returns the gradient w.r.t. the layer input (written to ``dx_out``).
+        ``prev``: the GroupNorm layer whose activation IS this layer's input and whose complete activation gradient
+        this call produces (data gradient + ``dx_addend``): where the kernel can, the first pass of ``prev``'s
+        GroupNorm backward (the sums over g and its raw output) is folded into the data-gradient epilogue."""
         be = self.be
         self._tag(L.wname)
         n, cout = L.y.shape[0], L.y.shape[-1]
@@ -279,7 +283,11 @@ class Engine:
             dgam, dbet = self._grad_view(L.gname + ".weight"), self._grad_view(L.gname + ".bias")
             dbia = self._grad_view(L.bname) if L.bname is not None else None
             fused = getattr(be, "gn_bwd_fused_ok", None)
-            if fused is not None and fused(g_act, L.y, dy):
+            if L.pre_sums is not None:
+                # the conv that produced g_act has already accumulated sum g*m and sum g*m*y in its epilogue
+                be.gn_bwd_apply_gn(g_act, L.y, L.gn, L.pre_sums, dy, dgam, dbet, dbia, sum_y_from_stats=True)
+                L.pre_sums = None
+            elif fused is not None and fused(g_act, L.y, dy):
                 # small levels: reduce -> grid barrier -> apply in one launch (sums + one zeroed barrier word)
                 buf = self.zeros((n * cout * 3 + 2,), torch.float64, dev)
                 be.gn_bwd_fused_gn(g_act, L.y, L.gn, buf[:n * cout * 3].view(n, cout, 3), buf[n * cout * 3:], dy,
@@ -330,7 +338,14 @@ class Engine:
         dkind = {K3: K3, K1: K1, DOWN: UP, UP: DOWN}[L.kind]
         if dx_out is None:
             dx_out = torch.empty(L.x.shape, dtype=self.T, device=dev)
-        be.conv(dkind, self.dims, dy, wd, None, dx_out, None, dx_addend)
+        ok = getattr(be, "conv_bwdstats_ok", None)
+        if (prev is not None and prev.gn is not None and prev.gname is not None and ok is not None
+                and prev.y.shape == dx_out.shape and ok(dkind, self.dims, dy, wd, dx_out, dx_addend, prev.y)):
+            self._tag(prev.wname)
+            prev.pre_sums = self.zeros((prev.y.shape[0], prev.y.shape[-1], 3), torch.float64, dev)
+            be.conv_bwdstats(dkind, self.dims, dy, wd, dx_out, dx_addend, prev.y, prev.gn, prev.pre_sums)
+        else:
+            be.conv(dkind, self.dims, dy, wd, None, dx_out, None, dx_addend)
         return dx_out
 
     def alloc_grads(self, device) -> Tensor:
@@ -460,7 +475,8 @@ class Engine:
             g_out = g                                    # d/d(out) ; out = ops(xcat) + xcat
             gh = g_out
             for j in reversed(range(len(ops))):
-                gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None)
+                gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None,
+                                    prev=ops[j - 1] if j > 0 else Lc)
             gcat = self.bwd_layer(Lc, gh, True)          # (N,..,2*co)
             co = Lu.y.shape[-1]
             gskip[i] = gcat[..., co:]
@@ -470,7 +486,8 @@ class Engine:
             g_out = g
             gh = g_out
             for j in reversed(range(len(ops))):
-                gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None)
+                gh = self.bwd_layer(ops[j], gh, True, dx_addend=g_out if j == 0 else None,
+                                    prev=ops[j - 1] if j > 0 else Ld)
             g = self.bwd_layer(Ld, gh, True, dx_addend=gskip[i])
             if i == 3:
                 self._flush_bucket("down_tr256.down_conv.weight")
@@ -555,20 +572,20 @@ class Engine:
         for i in (0, 1, 2, 3):
             k = i + 1
             L1, L2 = sv[f"decoder{k}"]
-            g1 = self.bwd_layer(L2, g, True)
+            g1 = self.bwd_layer(L2, g, True, prev=L1)
             gcat = self.bwd_layer(L1, g1, True)
             co = L2.y.shape[-1]
             genc[i] = gcat[..., co:]
             g = self.bwd_layer(sv[f"upconv{k}"], gcat[..., :co], True)
         L1, L2 = sv["bottleneck"]
-        g = self.bwd_layer(L1, self.bwd_layer(L2, g, True), True)
+        g = self.bwd_layer(L1, self.bwd_layer(L2, g, True, prev=L1), True)
         self._flush_bucket("bottleneck.bottleneckconv1.weight")
         for i in (3, 2, 1, 0):
             e, pooled = sv[f"pool{i + 1}"]
             ge = torch.empty(e.shape, dtype=self.T, device=e.device)
             self.be.pool_bwd(e, g, genc[i], ge, self.dims)               # + gradient from the skip concat
             L1, L2 = sv[f"encoder{i + 1}"]
-            g1 = self.bwd_layer(L2, ge, True)
+            g1 = self.bwd_layer(L2, ge, True, prev=L1)
             g = self.bwd_layer(L1, g1, i > 0)
         self._finish_backward()
         return flat

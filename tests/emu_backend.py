@@ -95,6 +95,17 @@ class EmuBackend:
             out = out + _ncdhw(addend)
         _store(y, out)
 
+    def conv_bwdstats_ok(self, kind, dims, x, wpk, y, addend, yfwd):
+        return kind == K3
+
+    def conv_bwdstats(self, kind, dims, x, wpk, y, addend, yfwd, gn, sums):
+        """the data-gradient conv, then the first two backward sums of the layer (yfwd, gn) on the STORED g; sums[..,2]
+        (sum of yfwd) is left alone: gn_bwd_apply_gn(sum_y_from_stats=True) takes it from the forward statistics"""
+        self.conv(kind, dims, x, wpk, None, y, None, addend)
+        tmp = torch.zeros_like(sums)
+        self.gn_bwd_reduce_gn(y, yfwd, gn, tmp)
+        sums[..., 0:2] += tmp[..., 0:2]
+
     def wgrad(self, kind, dims, a, b, dwp):
         """dwp[t][ka][kb] += sum_{n,o} a[n, o*s + t - p, ka] * b[n, o, kb]"""
         k = _ktuple(kind, dims)
@@ -149,9 +160,12 @@ class EmuBackend:
         coef, _ = self._coef(gn, y.shape[0], y.shape[-1])
         self.gn_bwd_reduce(g, y, coef, sums)
 
-    def gn_bwd_apply_gn(self, g, y, gn, sums, dy, dgamma, dbeta, dbias):
+    def gn_bwd_apply_gn(self, g, y, gn, sums, dy, dgamma, dbeta, dbias, sum_y_from_stats=False):
         n, c = y.shape[0], y.shape[-1]
         stats, gamma, beta, scale, vox, groups, eps = gn
+        if sum_y_from_stats:
+            sums = sums.clone()
+            sums[..., 2] = stats[..., 0]
         coef, mr = self._coef(gn, n, c)
         coef3 = torch.empty(n, c, 3)
         self.gn_bwd_finalize(sums, mr, gamma, scale, vox, groups, coef3, dgamma, dbeta, dbias)

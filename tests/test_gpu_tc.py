@@ -311,3 +311,58 @@ def test_halo_ws_conv_matches_emulation(be, n, sp, cin, cout, which):
         assert float(ybuf[..., :16].abs().max()) == 0 and float(ybuf[..., 16 + co:].abs().max()) == 0
         if with_stats:
             assert rel(st_c, st_e) < 1e-4
+
+
+@pytest.mark.parametrize("n,sp,cin,cout,with_addend,with_scale", [
+    (2, (12, 32, 24), 16, 16, True, True),
+    (1, (9, 20, 12), 32, 32, False, False),       # ragged tile, one CTA per SM variant
+    (2, (40, 48, 48), 32, 16, True, True),        # more items than CTAs, both samples, ring wrap
+    (1, (6, 16, 8), 16, 32, True, False),
+])
+def test_conv_bwdstats_equals_conv_plus_reduce(be, n, sp, cin, cout, with_addend, with_scale):
+    """b200seg_conv_bwdstats: the data-gradient conv whose epilogue accumulates the GroupNorm-backward sums of the
+    layer behind its output == b200seg_conv followed by b200seg_gn_bwd_reduce_gn (sums [..][0:2]; [2] untouched)."""
+    g = torch.Generator().manual_seed(21)
+    dt = torch.bfloat16
+    w = torch.randn((cin, cout, 3, 3, 3), generator=g) * (2.0 / (cin * 27)) ** 0.5     # conv (Co=cin.. ) dgrad form
+    dy = torch.randn((n,) + sp + (cin,), generator=g).to(dt).cuda()                      # gradient of the consumer layer
+    wp = be.pack_weight(w.cuda(), K3, "dgrad", dt, 3, vox=10 ** 9)                       # dgrad: cin(out ch of fwd) -> cout
+    assert wp.code == 3
+    yfwd = torch.randn((n,) + sp + (cout,), generator=g).to(dt).cuda()                   # raw conv output of the producer
+    add = torch.randn((n,) + sp + (cout,), generator=g).to(dt).cuda() if with_addend else None
+    yf = yfwd.float()
+    stats = torch.stack([yf.sum((1, 2, 3)).double(), (yf * yf).sum((1, 2, 3)).double()], -1).contiguous()
+    gamma = (1 + 0.2 * torch.randn(cout, generator=g)).cuda()
+    beta = (0.3 * torch.randn(cout, generator=g)).cuda()
+    scale = (torch.rand((n, cout), generator=g) > 0.2).float().div(0.8).cuda() if with_scale else None
+    vox = sp[0] * sp[1] * sp[2]
+    gn = (stats, gamma, beta, scale, vox, 8, 1e-5)
+    # reference: two launches
+    g_ref = torch.empty((n,) + sp + (cout,), dtype=dt, device="cuda")
+    be.conv(K3, 3, dy, wp, None, g_ref, None, add)
+    sums_ref = torch.zeros(n, cout, 3, dtype=torch.float64, device="cuda")
+    be.gn_bwd_reduce_gn(g_ref, yfwd, gn, sums_ref)
+    # fused
+    g_out = torch.empty_like(g_ref)
+    if cout == 32:
+        assert be.conv_bwdstats_ok(K3, 3, dy, wp, g_out, add, yfwd)
+    # (16 output channels: the engine does not pick the fused form -- it measured slower -- but the kernel exists and
+    #  must be right; B200SEG_BWDSTATS_ALL=1 enables it)
+    sums = torch.zeros(n, cout, 3, dtype=torch.float64, device="cuda")
+    be.conv_bwdstats(K3, 3, dy, wp, g_out, add, yfwd, gn, sums)
+    torch.cuda.synchronize()
+    assert torch.equal(g_out, g_ref)
+    assert float(sums[..., 2].abs().max()) == 0.0
+    scale_ = sums_ref[..., 0:2].abs().max(dim=0, keepdim=True).values + 1e-9
+    assert ((sums[..., 0:2] - sums_ref[..., 0:2]).abs() / scale_).max() < 2e-5
+    # the apply pass with sum y taken from the forward statistics == the apply pass on the three-sum buffer
+    outs = []
+    for s_, flag in ((sums_ref, False), (sums, True)):
+        dyo = torch.empty_like(g_ref)
+        dg, db, dbi = (torch.zeros(cout, device="cuda") for _ in range(3))
+        be.gn_bwd_apply_gn(g_out, yfwd, gn, s_, dyo, dg, db, dbi, sum_y_from_stats=flag)
+        outs.append((dyo.float(), dg, db, dbi))
+    torch.cuda.synchronize()
+    assert rel(outs[1][0], outs[0][0]) < 1e-3
+    for a, b in zip(outs[1][1:], outs[0][1:]):
+        assert (a - b).abs().max() < 2e-4 * (1 + b.abs().max())
