@@ -221,14 +221,6 @@ int b200seg_conv_bwdstats_supported(int kind, int dims, const b200seg_tensor* x,
                                     const b200seg_tensor* addend, const b200seg_tensor* yfwd) {
   if (x == nullptr || y == nullptr || yfwd == nullptr) return 0;
   if (!conv_halo_bwdstats_ok(dims) || !conv_halo_supported(kind, dims, x, w_dtype, y, addend)) return 0;
-  // measured on B200 (VNet3d 96^3 step): with 32 output channels the fused form beats conv + reduce (42 vs 33.5 + 19.5 us
-  // at 48^3); with 16 it loses (125 vs 60 + 34 us at 96^3: the two-CTA kernel has no registers to spare and the layer
-  // is traffic bound once it also reads the producer's raw output).  B200SEG_BWDSTATS_ALL=1 lifts the restriction.
-  static const bool all = [] {
-    const char* e = getenv("B200SEG_BWDSTATS_ALL");
-    return e && e[0] == '1';
-  }();
-  if (y->c != 32 && !all) return 0;
   if (pw_mma_supported(kind, dims, x, w_dtype, y, addend) || conv_tc_supported(kind, dims, x, w_dtype, y, addend)) return 0;
   return (yfwd->n == y->n && yfwd->d == y->d && yfwd->h == y->h && yfwd->w == y->w && yfwd->c == y->c &&
           yfwd->dtype == B200SEG_BF16 && (yfwd->ld % 8) == 0 && (reinterpret_cast<uintptr_t>(yfwd->ptr) % 16) == 0)

@@ -346,8 +346,8 @@ def test_conv_bwdstats_equals_conv_plus_reduce(be, n, sp, cin, cout, with_addend
     g_out = torch.empty_like(g_ref)
     if cout == 32:
         assert be.conv_bwdstats_ok(K3, 3, dy, wp, g_out, add, yfwd)
-    # (16 output channels: the engine does not pick the fused form -- it measured slower -- but the kernel exists and
-    #  must be right; B200SEG_BWDSTATS_ALL=1 enables it)
+    else:   # 16 output channels: the engine does not pick the fused form (measured slower); the kernel must be right
+        assert not be.conv_bwdstats_ok(K3, 3, dy, wp, g_out, add, yfwd)
     sums = torch.zeros(n, cout, 3, dtype=torch.float64, device="cuda")
     be.conv_bwdstats(K3, 3, dy, wp, g_out, add, yfwd, gn, sums)
     torch.cuda.synchronize()
