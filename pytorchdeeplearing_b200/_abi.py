@@ -330,12 +330,13 @@ class CudaBackend:
 
     def conv_bwdstats_ok(self, kind, dims, x, wpk, y, addend, yfwd):
         """can ``conv_bwdstats`` take this data-gradient convolution (3-D halo-staged 16/32-channel 3x3x3 layers)?"""
-        if not self.fused_bwd_stats or wpk.code != BF16_HALO or x.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
+        if (not self.fused_bwd_stats or wpk.code not in (BF16_HALO, BF16_HALO_WS) or x.dtype != torch.bfloat16
+                or y.dtype != torch.bfloat16):
             return False
         # measured on B200 (VNet3d 96^3 step): with 32 output channels the fused form beats conv + reduce (42 vs
         # 33.5 + 19.5 us at 48^3); with 16 it loses (125 vs 60 + 34 us at 96^3: the two-CTA kernel has no registers to
         # spare and the layer is traffic bound once it also reads the producer's raw output)
-        if y.shape[-1] != 32 and os.environ.get("B200SEG_BWDSTATS_ALL", "0") != "1":
+        if y.shape[-1] == 16 and os.environ.get("B200SEG_BWDSTATS_ALL", "0") != "1":
             return False
         dx, dy, da, df = _desc(x), _desc(y), _desc(addend), _desc(yfwd)
         return bool(self.lib.b200seg_conv_bwdstats_supported(kind, dims, C.byref(dx), wpk.code, C.byref(dy), _ref(da),

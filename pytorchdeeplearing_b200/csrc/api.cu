@@ -39,7 +39,8 @@ int conv_halows_ntile(int kind, int cin, int cout);
 int conv_halows_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
                           const b200seg_tensor* addend);
 int conv_halows(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias,
-                const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device, cudaStream_t st);
+                const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device, cudaStream_t st,
+                const b200seg_tensor* yfwd = nullptr, const b200seg_gn* gn = nullptr, double* sums = nullptr);
 int conv_tc_channels_ok(int kind, int cin, int cout);
 int smallcin_conv_supported(int kind, const b200seg_tensor* x, const b200seg_tensor* y, const b200seg_tensor* addend);
 int smallcin_conv(int kind, int dims, const b200seg_tensor* x, const void* w, int w_dtype, const float* bias,
@@ -217,11 +218,20 @@ int b200seg_conv(int kind, int dims, const b200seg_tensor* x, const void* wpk, i
   return conv_generic(kind, dims, x, wpk, w_dtype, bias, y, stats, addend, ST(stream));
 }
 
+static int bwdstats_path(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
+                         const b200seg_tensor* addend) {
+  // 1: halo3 (16/32 channels, 3-D), 2: halo-ws (64/128 channels), 0: none -- and only where b200seg_conv itself would
+  // take that kernel
+  if (pw_mma_supported(kind, dims, x, w_dtype, y, addend) || conv_tc_supported(kind, dims, x, w_dtype, y, addend)) return 0;
+  if (conv_halo_supported(kind, dims, x, w_dtype, y, addend)) return conv_halo_bwdstats_ok(dims) ? 1 : 0;
+  if (conv_halows_supported(kind, dims, x, w_dtype, y, addend)) return 2;
+  return 0;
+}
+
 int b200seg_conv_bwdstats_supported(int kind, int dims, const b200seg_tensor* x, int w_dtype, const b200seg_tensor* y,
                                     const b200seg_tensor* addend, const b200seg_tensor* yfwd) {
   if (x == nullptr || y == nullptr || yfwd == nullptr) return 0;
-  if (!conv_halo_bwdstats_ok(dims) || !conv_halo_supported(kind, dims, x, w_dtype, y, addend)) return 0;
-  if (pw_mma_supported(kind, dims, x, w_dtype, y, addend) || conv_tc_supported(kind, dims, x, w_dtype, y, addend)) return 0;
+  if (bwdstats_path(kind, dims, x, w_dtype, y, addend) == 0) return 0;
   return (yfwd->n == y->n && yfwd->d == y->d && yfwd->h == y->h && yfwd->w == y->w && yfwd->c == y->c &&
           yfwd->dtype == B200SEG_BF16 && (yfwd->ld % 8) == 0 && (reinterpret_cast<uintptr_t>(yfwd->ptr) % 16) == 0)
              ? 1 : 0;
@@ -240,6 +250,8 @@ int b200seg_conv_bwdstats(int kind, int dims, const b200seg_tensor* x, const voi
                  "b200seg_conv_bwdstats: unsupported shape (query b200seg_conv_bwdstats_supported first)");
   B200_DEVICE(device);
   if (conv_tc_init(device) != B200SEG_OK) return B200SEG_ECUDA;
+  if (bwdstats_path(kind, dims, x, w_dtype, y, addend) == 2)
+    return conv_halows(kind, dims, x, wpk, nullptr, y, nullptr, addend, device, ST(stream), yfwd, gn, sums);
   return conv_halo(kind, dims, x, wpk, nullptr, y, nullptr, addend, device, ST(stream), yfwd, gn, sums);
 }
 

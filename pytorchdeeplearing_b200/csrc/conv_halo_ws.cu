@@ -44,6 +44,16 @@ struct HaloWsArgs {
   int nslices;            // ring size (>= NACC + 2)
   int wstages;            // weight ring depth (tap blocks in flight)
   int tmem_cols;
+  // GroupNorm-backward sums fused into the data-gradient epilogue (b200seg_conv_bwdstats; see conv_halo.cu)
+  const bf16* yfwd;
+  long long yfld;
+  const double* gstats;
+  const float* ggamma;
+  const float* gbeta;
+  const float* gscale;
+  int ggroups;
+  double gm;
+  float geps;
   unsigned long long* dbg;   // development aid: %globaltimer stamps of CTA 0 (null in production)
 };
 
@@ -59,7 +69,7 @@ __device__ __forceinline__ uint64_t ws_nosw_desc(uint32_t lbo_bytes, uint32_t sb
   return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 
-template <int CIN, int NT, int NACC>
+template <int CIN, int NT, int NACC, bool BWD>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWsArgs p) {
   PDL_ENTER();
   constexpr int CP = CIN / 8;                                // 8-channel planes
@@ -82,6 +92,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWs
   uint64_t* wempty = wfull + kWsMaxWStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty + kWsMaxWStages);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][2][Cout]
+  float* s_ab = s_stat + 8 * p.Cout;                         // [2][Cout]: A, B of the sample being processed (BWD)
+  double* s_gd = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_ab + 2 * p.Cout) + 7) & ~(uintptr_t)7);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -283,8 +295,40 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWs
             t += (double)s_stat[wq * 2 * p.Cout + i];
             s_stat[wq * 2 * p.Cout + i] = 0.f;
           }
-          atomicAdd(p.stats + ((long long)n * p.Cout + c) * 2 + which, t);
+          atomicAdd(p.stats + ((long long)n * p.Cout + c) * (BWD ? 3 : 2) + which, t);
         }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    // A, B of sample n for the ReLU mask of the backward sums: same expressions and precision as gn_cta_coefs
+    auto load_coefs = [&](int n) {
+      const int C = p.Cout, cpg = C / p.ggroups;
+      for (int c = etid; c < C; c += 128) {
+        const double* q_ = p.gstats + ((long long)n * C + c) * 2;
+        s_gd[c] = q_[0];
+        s_gd[C + c] = q_[1];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (etid < p.ggroups) {
+        double sm = 0.0, sq = 0.0;
+        for (int k_ = 0; k_ < cpg; ++k_) {
+          sm += s_gd[etid * cpg + k_];
+          sq += s_gd[C + etid * cpg + k_];
+        }
+        const double mean = sm / p.gm;
+        double var = sq / p.gm - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_gd[2 * C + etid * 2 + 0] = mean;
+        s_gd[2 * C + etid * 2 + 1] = rsqrt(var + (double)p.geps);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = etid; c < C; c += 128) {
+        const int g_ = c / cpg;
+        const double mean = s_gd[2 * C + g_ * 2 + 0], rstd = s_gd[2 * C + g_ * 2 + 1];
+        const double sc = p.gscale ? (double)p.gscale[(long long)n * C + c] : 1.0;
+        const double ga = (double)p.ggamma[c], be = (double)p.gbeta[c];
+        s_ab[c] = (float)(rstd * ga * sc);
+        s_ab[C + c] = (float)((be - mean * rstd * ga) * sc);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -294,6 +338,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWs
       if (n != cur_n) {
         if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
         cur_n = n;
+        if constexpr (BWD) load_coefs(n);
       }
       const int oh = h0 + rh, ow = w0 + rw;
       const bool valid = oh < p.H && ow < p.W;
@@ -316,14 +361,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWs
         }
         for (int o = 0; o < nd; ++o) {
           const long long vox = (((long long)n * p.D + (d0 + o)) * p.H + oh) * p.W + ow;
+          uint4 yfv[2];
+          if constexpr (BWD) {
+            yfv[0] = yfv[1] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+              yfv[0] = *reinterpret_cast<const uint4*>(p.yfwd + vox * p.yfld + c0);
+              yfv[1] = *reinterpret_cast<const uint4*>(p.yfwd + vox * p.yfld + c0 + 8);
+            }
+          }
           float v[16];
           tmem_ld16(tacc + (uint32_t)(o * NT + c * 16), v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             v[j] += bv[j];
-            const float sv = valid ? v[j] : 0.f;
-            rs[j] += sv;
-            rq[j] = fmaf(sv, sv, rq[j]);
+            if constexpr (!BWD) {
+              const float sv = valid ? v[j] : 0.f;
+              rs[j] += sv;
+              rq[j] = fmaf(sv, sv, rq[j]);
+            }
           }
           if (valid) {
             if (p.addend != nullptr) {
@@ -333,8 +388,38 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWs
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] += r[j];
             }
-            store8(p.y + vox * p.yld + c0, v);
-            store8(p.y + vox * p.yld + c0 + 8, v + 8);
+            if constexpr (!BWD) {
+              store8(p.y + vox * p.yld + c0, v);
+              store8(p.y + vox * p.yld + c0 + 8, v + 8);
+            } else {
+              // g is rounded to bf16 once: what is stored is what the sums see (as a separate reduce pass would)
+#pragma unroll
+              for (int h_ = 0; h_ < 2; ++h_) {
+                uint4 pk;
+                __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g2[j] = __floats2bfloat162_rn(v[8 * h_ + 2 * j], v[8 * h_ + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(p.y + vox * p.yld + c0 + 8 * h_) = pk;
+                const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yfv[h_]);
+                const int cb = c0 + 8 * h_;
+                const float4 a0 = *reinterpret_cast<const float4*>(s_ab + cb), a1 = *reinterpret_cast<const float4*>(s_ab + cb + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(s_ab + p.Cout + cb);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_ab + p.Cout + cb + 4);
+                const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 yy = __bfloat1622float2(y2[j]);
+                  const float2 gg = __bfloat1622float2(g2[j]);
+                  const float d0_ = fmaf(yy.x, aa[2 * j], bb[2 * j]) > 0.f ? gg.x : 0.f;
+                  const float d1_ = fmaf(yy.y, aa[2 * j + 1], bb[2 * j + 1]) > 0.f ? gg.y : 0.f;
+                  rs[8 * h_ + 2 * j] += d0_;
+                  rs[8 * h_ + 2 * j + 1] += d1_;
+                  rq[8 * h_ + 2 * j] = fmaf(d0_, yy.x, rq[8 * h_ + 2 * j]);
+                  rq[8 * h_ + 2 * j + 1] = fmaf(d1_, yy.y, rq[8 * h_ + 2 * j + 1]);
+                }
+              }
+            }
           }
         }
         if (c == NT / 16 - 1) {
@@ -408,9 +493,11 @@ static int g_ws_init[64] = {0};
 
 template <int CIN, int NT, int NACC>
 static int conv_halows_launch(HaloWsArgs& p, int device, int maxsm, cudaStream_t st) {
+  // (tail: + A/B table and its fp64 scratch for the backward-sums epilogue)
   const uint32_t slice = (uint32_t)(CIN / 8) * WS_PH * WS_PW * 16u;
   const uint32_t tap_bytes = (uint32_t)CIN * NT * 2u;
-  const uint32_t tail = (2 * kWsMaxSlices + 4 + 2 * kWsMaxWStages) * 8 + 16 + 8 * p.Cout * 4 + 64;
+  const uint32_t tail = (2 * kWsMaxSlices + 4 + 2 * kWsMaxWStages) * 8 + 16 + 10 * p.Cout * 4 + 64 +
+                        (2 * p.Cout + 16) * 8 + 8;
   // one item's slices stay resident; everything left goes to the weight ring (tap blocks in flight hide the
   // L2 latency of the stream: each block is consumed in ~0.1 us)
   const int ns = NACC + 2;
@@ -429,18 +516,22 @@ static int conv_halows_launch(HaloWsArgs& p, int device, int maxsm, cudaStream_t
   const size_t smem_bytes = 128 + wbytes + (size_t)ns * slice + tail;
   const int sms = num_sms(device);
   const int grid = sms < p.nitems ? sms : p.nitems;
-  launch_k(conv_halows_kernel<CIN, NT, NACC>, grid, kWsThreads, smem_bytes, st, p);
+  if (p.yfwd != nullptr) launch_k(conv_halows_kernel<CIN, NT, NACC, true>, grid, kWsThreads, smem_bytes, st, p);
+  else launch_k(conv_halows_kernel<CIN, NT, NACC, false>, grid, kWsThreads, smem_bytes, st, p);
   B200_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
 int conv_halows(int kind, int dims, const b200seg_tensor* x, const void* wpk, const float* bias,
-                const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device, cudaStream_t st) {
+                const b200seg_tensor* y, double* stats, const b200seg_tensor* addend, int device, cudaStream_t st,
+                const b200seg_tensor* yfwd, const b200seg_gn* gn, double* sums) {
   (void)kind; (void)dims;
   const int maxsm = tc_max_smem(device);
   if (device >= 0 && device < 64 && !g_ws_init[device]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_halows_kernel<64, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-    B200_CUDA(cudaFuncSetAttribute(conv_halows_kernel<128, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    B200_CUDA(cudaFuncSetAttribute(conv_halows_kernel<64, 64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    B200_CUDA(cudaFuncSetAttribute(conv_halows_kernel<128, 64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    B200_CUDA(cudaFuncSetAttribute(conv_halows_kernel<64, 64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    B200_CUDA(cudaFuncSetAttribute(conv_halows_kernel<128, 64, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     g_ws_init[device] = 1;
   }
   HaloWsArgs p;
@@ -455,6 +546,21 @@ int conv_halows(int kind, int dims, const b200seg_tensor* x, const void* wpk, co
   p.Cin = x->c; p.Cout = y->c;
   p.tw = (p.W + WS_TW - 1) / WS_TW;
   p.th = (p.H + WS_TH - 1) / WS_TH;
+  p.yfwd = nullptr; p.yfld = 0; p.gstats = nullptr; p.ggamma = nullptr; p.gbeta = nullptr; p.gscale = nullptr;
+  p.ggroups = 1; p.gm = 1.0; p.geps = 0.f;
+  if (yfwd != nullptr) {
+    B200_CHECK_ARG(gn != nullptr && sums != nullptr && stats == nullptr && same_geom(yfwd, y) &&
+                       yfwd->dtype == B200SEG_BF16 && (yfwd->ld % 8) == 0 && al16w(yfwd->ptr) && gn->groups > 0 &&
+                       gn->groups <= 8 && (y->c % gn->groups) == 0,
+                   "conv_halows: bad forward tensor / GroupNorm reference for the backward statistics");
+    p.yfwd = static_cast<const bf16*>(yfwd->ptr);
+    p.yfld = yfwd->ld;
+    p.gstats = gn->stats; p.ggamma = gn->gamma; p.gbeta = gn->beta; p.gscale = gn->scale;
+    p.ggroups = gn->groups;
+    p.gm = (double)(y->c / gn->groups) * (double)gn->vox;
+    p.geps = gn->eps;
+    p.stats = sums;
+  }
   {
     // B200SEG_WS_DBG=<device pointer, hex>: 8 x u64 time stamps of CTA 0 (tools/ws_timeline.py)
     const char* e = getenv("B200SEG_WS_DBG");
