@@ -18,6 +18,8 @@
 // contiguous tile ranges (grid = min(tiles, #SM)).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "tc_common.cuh"
 
 namespace b200seg {
@@ -62,6 +64,12 @@ struct TcArgs {
   int nstages;
   int nacc;               // accumulator stages in TMEM (2 or 4)
   int tmem_cols;          // power of two >= nacc*Ntile (>= 32)
+  // split-K (deep, small levels): the (tap, channel-block) loop of one (voxel tile, column group) is cut into
+  // `ksplit` ranges, one work item each; every item leaves its fp32 partial in its own slab of `ws`, and the item
+  // that arrives last (counted in cnt[tile, group]) adds the slabs in split order and runs the usual epilogue
+  int ksplit;
+  float4* ws;             // [tile*group][ksplit][Ntile/4][128 rows] float4
+  unsigned int* cnt;      // [tile*group], zero between launches (the last arriver resets its word)
 };
 
 constexpr int kMaxStages = 8;
@@ -116,12 +124,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint64_t* tempty = tfull + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);     // [2 groups][4 epilogue warps][2][Cout]
+  unsigned int* s_flag = reinterpret_cast<unsigned int*>(s_stat + 8 * kEpiGroups * p.Cout);   // [2 groups]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work item = (voxel tile, column group); consecutive items of a CTA share the voxel tile
-  const int nitems = p.ntiles * p.ngroups;
+  // work item = (voxel tile, column group, K range); consecutive items of a CTA share the voxel tile
+  const int S = p.ksplit;
+  const int nitems = p.ntiles * p.ngroups * S;
   const int items_per_cta = (nitems + gridDim.x - 1) / gridDim.x;
   const int tile_begin = blockIdx.x * items_per_cta;
   const int tile_end = min(nitems, tile_begin + items_per_cta);
@@ -156,27 +166,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (elect_one()) {
       uint32_t it = 0;
       for (int item = tile_begin; item < tile_end; ++item) {
-        int t = item / p.ngroups;
-        const int ng = item - t * p.ngroups;
+        const int sp = item % S;
+        const int tg = item / S;
+        int t = tg / p.ngroups;
+        const int ng = tg - t * p.ngroups;
         const int iw = t % p.tw; t /= p.tw;
         const int ih = t % p.th; t /= p.th;
         const int id = t % p.td;
         const int n = t / p.td;
         const int w0 = iw * p.bw * p.sw, h0 = ih * p.bh * p.sh, d0 = id * p.bd * p.sd;
-        int tap = 0;
-        for (int kd_ = 0; kd_ < p.kd; ++kd_)
-          for (int kh_ = 0; kh_ < p.kh; ++kh_)
-            for (int kw_ = 0; kw_ < p.kw; ++kw_, ++tap) {
-              for (int cb = 0; cb < cblocks; ++cb, ++it) {
-                const uint32_t s = it % p.nstages;
-                const uint32_t ph = (it / p.nstages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                uint8_t* sa = smem + (size_t)s * STAGE;
-                mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
-                tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
-                tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout + ng * p.Ntile);
-              }
-            }
+        const int kb0 = sp * kblocks / S, kb1 = (sp + 1) * kblocks / S;
+        int tap = kb0 / cblocks, cb = kb0 - tap * cblocks;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kd_ = tap / (p.kw * p.kh);
+          const uint32_t s = it % p.nstages;
+          const uint32_t ph = (it / p.nstages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * STAGE;
+          mbar_expect_tx(&full[s], A_BYTES + b_bytes_real);
+          tma_load_5d(&tmA, sa, &full[s], cb * BKC, w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, n);
+          tma_load_2d(&tmB, sa + A_BYTES, &full[s], cb * BKC, p.up ? ng * p.Ntile : tap * p.Cout + ng * p.Ntile);
+          if (++cb == cblocks) {
+            cb = 0;
+            ++tap;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -190,7 +204,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * (uint32_t)p.Ntile;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+      const int sp = item % S;
+      const int kb0 = sp * kblocks / S, kb1 = (sp + 1) * kblocks / S;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const uint32_t s = it % p.nstages;
         const uint32_t ph = (it / p.nstages) & 1u;
         mbar_wait(&full[s], ph);
@@ -202,10 +218,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < BKC / 16; ++k) {
             // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
-            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);
-          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+          if (kb == kb1 - 1) umma_commit(&tfull[as]);
         }
         __syncwarp();
       }
@@ -264,16 +281,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
     };
     for (int item = tile_begin + eg, local = eg; item < tile_end; item += kEpiGroups, local += kEpiGroups) {
-      int t = item / p.ngroups;
-      const int ng = item - t * p.ngroups;
+      const int sp = item % S;
+      const int tg = item / S;
+      int t = tg / p.ngroups;
+      const int ng = tg - t * p.ngroups;
       const int iw = t % p.tw; t /= p.tw;
       const int ih = t % p.th; t /= p.th;
       const int id = t % p.td;
       const int n = t / p.td;
-      if (n != cur_n) {
-        if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
-        cur_n = n;
-      }
       const int ow = iw * p.bw + rw, oh = ih * p.bh + rh, od = id * p.bd + rd;
       const bool valid = ow < p.W && oh < p.H && od < p.D;
       const long long vox = (((long long)n * p.D + od) * p.H + oh) * p.W + ow;
@@ -282,9 +297,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * (uint32_t)p.Ntile + ((uint32_t)(q * 32) << 16);
+      const float4* slabs = nullptr;
+      if (S > 1) {
+        // partial sums of this K range -> own slab; the accumulator is free as soon as it has been read
+        float4* mine = p.ws + ((size_t)tg * S + sp) * (size_t)(p.Ntile / 4) * 128 + row;
+        for (int cc = 0; cc < p.Ntile; cc += 16) {
+          float v[16];
+          tmem_ld16(tacc + (uint32_t)cc, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            __stcg(mine + (size_t)(cc / 4 + j) * 128, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        __threadfence();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        if (etid == 0) s_flag[eg] = atomicAdd(p.cnt + tg, 1u);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        if (s_flag[eg] != (unsigned int)(S - 1)) continue;      // not the last K range of this (tile, group) to finish
+        __threadfence();
+        if (etid == 0) p.cnt[tg] = 0u;                           // ready for the next launch
+        slabs = p.ws + (size_t)tg * S * (size_t)(p.Ntile / 4) * 128 + row;
+      }
+      if (n != cur_n) {
+        if (cur_n >= 0 && p.stats != nullptr) flush_stats(cur_n);
+        cur_n = n;
+      }
       for (int cc = 0; cc < p.Ntile; cc += 16) {
         float v[16];
-        tmem_ld16(tacc + (uint32_t)cc, v);
+        if (S == 1) {
+          tmem_ld16(tacc + (uint32_t)cc, v);
+        } else {
+          // fixed order over the K ranges: the result does not depend on which range finished last
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll 2
+          for (int s_ = 0; s_ < S; ++s_) {
+            const float4* sl = slabs + (size_t)s_ * (size_t)(p.Ntile / 4) * 128 + (size_t)(cc / 4) * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 f = __ldcg(sl + (size_t)j * 128);
+              v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+            }
+          }
+        }
         // channel block of this 16-column chunk (UP: columns are (tap, cout); otherwise column group ng of Cout)
         int c0 = ng * p.Ntile + cc;
         long long ovox = vox;
@@ -343,9 +400,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           store8(p.y + ovox * p.yld + c0 + 8, v + 8);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (S == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+      }
     }
     if (p.stats != nullptr && cur_n >= 0) flush_stats(cur_n);
   }
@@ -417,6 +476,38 @@ void tc_pick_box(int W, int H, int D, int* bw, int* bh, int* bd) {
 
 static int g_smem_optin[64] = {0};
 
+// split-K scratch: kKsPool slabs per device, handed to streams in order of first use (no CUDA call at hand-out time, so
+// a stream first seen during graph capture still gets one); launches on one stream are ordered, so they share a slab
+constexpr int kKsPool = 4;
+constexpr size_t kKsBytes = 12u << 20;
+constexpr int kKsCntWords = 1024;
+struct KsSlab {
+  void* base = nullptr;
+  cudaStream_t owner = nullptr;
+  bool taken = false;
+};
+static KsSlab g_ks[64][kKsPool];
+static std::mutex g_ks_mutex;
+
+static bool ks_workspace(int device, cudaStream_t st, float4** ws, unsigned int** cnt) {
+  if (device < 0 || device >= 64) return false;
+  std::lock_guard<std::mutex> lock(g_ks_mutex);
+  for (int i = 0; i < kKsPool; ++i) {
+    KsSlab& k = g_ks[device][i];
+    if (k.base == nullptr) return false;
+    if (!k.taken) {
+      k.taken = true;
+      k.owner = st;
+    }
+    if (k.owner == st) {
+      *cnt = static_cast<unsigned int*>(k.base);
+      *ws = reinterpret_cast<float4*>(static_cast<char*>(k.base) + kKsCntWords * sizeof(unsigned int));
+      return true;
+    }
+  }
+  return false;
+}
+
 int wgrad_tc_init(int device, int maxsm);
 int tc_max_smem(int device) { return (device >= 0 && device < 64 && g_smem_optin[device] > 0) ? g_smem_optin[device] : 227 * 1024; }
 
@@ -432,6 +523,16 @@ int conv_tc_init(int device) {
   TC_ATTR(64, 0); TC_ATTR(64, 1); TC_ATTR(64, 2);
 #undef TC_ATTR
   if (wgrad_tc_init(device, maxsm) != B200SEG_OK) return B200SEG_ECUDA;
+  for (int i = 0; i < kKsPool; ++i) {
+    void* base = nullptr;
+    const size_t bytes = kKsCntWords * sizeof(unsigned int) + kKsBytes;
+    if (cudaMalloc(&base, bytes) != cudaSuccess || cudaMemset(base, 0, kKsCntWords * sizeof(unsigned int)) != cudaSuccess) {
+      cudaGetLastError();     // no scratch: the split-K form is simply not used
+      break;
+    }
+    std::lock_guard<std::mutex> lock(g_ks_mutex);
+    g_ks[device][i].base = base;
+  }
   g_smem_optin[device] = maxsm;
   return B200SEG_OK;
 }
@@ -458,14 +559,38 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const int ncols = g.up ? g.ud * g.uh * g.uw * p.Cout : p.Cout;
   p.Ntile = ncols > 256 ? 256 : ncols;
   p.ngroups = ncols / p.Ntile;
+  p.ksplit = 1;
+  p.ws = nullptr;
+  p.cnt = nullptr;
   {
-    // few voxel tiles (deep, small levels): split the output channels over more CTAs so the whole chip works
-    // on the layer; every group re-reads the activation tile (cheap, it is L2 resident) but only its own weights
+    // few voxel tiles (deep, small levels): spread the layer over the chip.  With a long (tap, channel-block) loop,
+    // cut the loop (split-K, column groups of >= 64 so the activation tile is not re-read more than needed); else
+    // split the output channels only: every group re-reads the activation tile (cheap, it is L2 resident) but only
+    // its own weights
     int bw_, bh_, bd_;
     tc_pick_box(p.W, p.H, p.D, &bw_, &bh_, &bd_);
     const int tiles = p.N * ((p.W + bw_ - 1) / bw_) * ((p.H + bh_ - 1) / bh_) * ((p.D + bd_ - 1) / bd_);
     const int sms = num_sms(device);
-    while (!g.up && tiles * p.ngroups * 2 <= sms && p.Ntile >= 64 && (p.Ntile / 2) % 16 == 0) {
+    const int kblocks = g.kd * g.kh * g.kw * (p.Cin / pick_bkc(p.Cin));
+    const char* e = getenv("B200SEG_TC_KSPLIT");          // 0: off, n >= 2: at most n ranges, unset: automatic
+    const int ks_max = e ? atoi(e) : 16;
+    if (!g.up && kblocks >= 16 && ks_max >= 2) {
+      int nt = p.Ntile, ngp = p.ngroups;
+      while (tiles * ngp * 2 <= sms && nt >= 128 && (nt / 2) % 16 == 0) {
+        nt /= 2;
+        ngp *= 2;
+      }
+      int S = sms / (tiles * ngp);
+      if (S > kblocks / 4) S = kblocks / 4;
+      if (S > ks_max) S = ks_max;
+      if (S >= 2 && tiles * ngp <= kKsCntWords && (size_t)tiles * ngp * S * 128 * nt * sizeof(float) <= kKsBytes &&
+          ks_workspace(device, st, &p.ws, &p.cnt)) {
+        p.Ntile = nt;
+        p.ngroups = ngp;
+        p.ksplit = S;
+      }
+    }
+    while (p.ksplit == 1 && !g.up && tiles * p.ngroups * 2 <= sms && p.Ntile >= 64 && (p.Ntile / 2) % 16 == 0) {
       p.Ntile /= 2;
       p.ngroups *= 2;
     }
@@ -480,7 +605,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
   const uint32_t a_bytes = 128u * swz;
   const uint32_t b_bytes = (((uint32_t)p.Ntile * swz) + 1023u) & ~1023u;
   const uint32_t stage = a_bytes + b_bytes;
-  const uint32_t tail = (2 * kMaxStages + 2 * kMaxAcc) * 8 + 16 + 8 * kEpiGroups * p.Cout * 4;
+  const uint32_t tail = (2 * kMaxStages + 2 * kMaxAcc) * 8 + 16 + 8 * kEpiGroups * p.Cout * 4 + 16;
   const int maxsm = g_smem_optin[device] > 0 ? g_smem_optin[device] : 227 * 1024;
   int nst = (int)((maxsm - 1024 - (int)tail - 256) / (int)stage);
   if (nst > kMaxStages) nst = kMaxStages;
@@ -521,7 +646,7 @@ int conv_tc(int kind, int dims, const b200seg_tensor* x, const void* wpk, const 
     B200_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
   int grid = num_sms(device);
-  if (grid > p.ntiles * p.ngroups) grid = p.ntiles * p.ngroups;
+  if (grid > p.ntiles * p.ngroups * p.ksplit) grid = p.ntiles * p.ngroups * p.ksplit;
   static const bool regstats_off = [] {
     const char* e = getenv("B200SEG_TC_REGSTATS");
     return e && e[0] == '0';

@@ -592,8 +592,8 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const T* __restrict__ y1,
 // that -- across the 8 warps, across CTAs -- is accumulated in fp64 in a fixed order (one private shared-memory
 // row per warp, then ONE fp64 global atomic per (channel, sum) per CTA).  The grid is sized to the resident CTAs
 // (3 per SM) and the voxel loop keeps two trips of loads in flight: the kernel is a pure HBM stream.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const T* __restrict__ g, long long ldg,
+template <typename T, int VEC, bool DEEP>
+__global__ void __launch_bounds__(256, DEEP ? 2 : 3) gn_bwd_reduce_kernel(const T* __restrict__ g, long long ldg,
                                                                const T* __restrict__ y, long long ldy,
                                                                const float* __restrict__ coef,
                                                                double* __restrict__ sums, int C, long long V,
@@ -631,6 +631,27 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const T* __restri
   }
   const T* yb = y + (long long)n * V * ldy + c0;
   const T* gb = g + (long long)n * V * ldg + c0;
+  if constexpr (DEEP) {
+    // four trips (eight 16-byte loads) in flight per thread: at two CTAs per SM that is 64 KB per SM on the wire,
+    // which is what it takes to keep HBM busy at ~1 us latency (the two-trip loop alone stalls at ~3.3 TB/s)
+    for (; vi + 3 * vstep < V; vi += 4 * vstep) {
+      float ya[4][VEC], ga[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        Vec<T, VEC>::load(yb + (vi + u * vstep) * ldy, ya[u]);
+        Vec<T, VEC>::load(gb + (vi + u * vstep) * ldg, ga[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float d = fmaf(ya[u][j], A[j], B[j]) > 0.f ? ga[u][j] : 0.f;
+          f1[j] += d;
+          f2[j] = fmaf(d, ya[u][j], f2[j]);
+          f3[j] += ya[u][j];
+        }
+    }
+  }
   for (; vi + vstep < V; vi += 2 * vstep) {
     float y0[VEC], g0[VEC], y1[VEC], g1[VEC];
     Vec<T, VEC>::load(yb + vi * ldy, y0);
@@ -1218,7 +1239,10 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
   const int C = y->c;
   EW_DISPATCH(y, vok, {
     const int G = C / VEC;
-    dim3 grid(ew_blocks(V, G, y->n, device, 3), y->n);
+    // large streams: deeper load pipeline, two CTAs per SM (B200SEG_GN_REDUCE_DEEP=0: the two-trip loop everywhere)
+    static const bool deep_on = [] { const char* e = getenv("B200SEG_GN_REDUCE_DEEP"); return !(e && e[0] == '0'); }();
+    const bool deep = deep_on && V * G >= (long long)num_sms(device) * 2 * 256 * 8;
+    dim3 grid(ew_blocks(V, G, y->n, device, deep ? 2 : 3), y->n);
     const bool pow2g = (G & (G - 1)) == 0;
     const int groups = (gn && gn->stats) ? gn->groups : 1;
     const size_t full = (3 * C + gn_cta_doubles(C, groups, false)) * sizeof(double) + (size_t)5 * C * sizeof(float);
@@ -1226,8 +1250,12 @@ int ew_gn_bwd_reduce(const b200seg_tensor* g, const b200seg_tensor* y, const flo
     const int staged = (pow2g && G <= 32 && staged_bytes <= 46 * 1024) ? 1 : 0;
     // precomputed-coefficient form without staging: only the [3][C] fp64 accumulators are touched (wide nets)
     const size_t base = (gn && gn->stats) ? full : (size_t)3 * C * sizeof(double);
-    launch_k(gn_bwd_reduce_kernel<T, VEC>, grid, 256, staged ? staged_bytes : base, s, static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
-        make_gnref(gn, C), staged);
+    if (deep)
+      launch_k(gn_bwd_reduce_kernel<T, VEC, true>, grid, 256, staged ? staged_bytes : base, s, static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
+          make_gnref(gn, C), staged);
+    else
+      launch_k(gn_bwd_reduce_kernel<T, VEC, false>, grid, 256, staged ? staged_bytes : base, s, static_cast<const T*>(g->ptr), g->ld, static_cast<const T*>(y->ptr), y->ld, coef, sums, C, V,
+          make_gnref(gn, C), staged);
   });
   B200_LAUNCH_CHECK();
   return B200SEG_OK;

@@ -168,7 +168,10 @@ class EmuBackend:
             sums[..., 2] = stats[..., 0]
         coef, mr = self._coef(gn, n, c)
         coef3 = torch.empty(n, c, 3)
-        self.gn_bwd_finalize(sums, mr, gamma, scale, vox, groups, coef3, dgamma, dbeta, dbias)
+        dbi = torch.zeros_like(dbias) if dbias is not None else None      # the fused form ACCUMULATES the bias gradient
+        self.gn_bwd_finalize(sums, mr, gamma, scale, vox, groups, coef3, dgamma, dbeta, dbi)
+        if dbias is not None:
+            dbias += dbi
         self.gn_bwd_apply(g, y, coef, coef3, dy)
 
     def apply(self, y1, c1, y2, c2, res, out):

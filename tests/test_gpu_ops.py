@@ -409,6 +409,39 @@ def test_groupnorm_backward_single_launch(be, dtype, n, sp, c, masked):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,sp,c", [(2, (64, 96, 96), 16), (1, (61, 83, 97), 16), (2, (48, 48, 47), 32)])
+def test_gn_bwd_reduce_large_streams(be, dtype, n, sp, c):
+    """the large-level form of gn_bwd_reduce_gn (four trips of loads in flight, two CTAs per SM) against a direct
+    fp64 statement of the three sums; ragged voxel counts exercise the four-trip / two-trip / single tails."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    y = torch.randn((n,) + sp + (c,), generator=g, device="cuda").to(dtype)
+    ga = torch.randn((n,) + sp + (c,), generator=g, device="cuda").to(dtype)
+    gamma = 1 + 0.2 * torch.randn(c, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(c, generator=g, device="cuda")
+    scale = (torch.rand(n, c, generator=g, device="cuda") > 0.2).float() / 0.8
+    vox = sp[0] * sp[1] * sp[2]
+    yd = y.double()
+    stats = torch.stack([yd.sum((1, 2, 3)), (yd * yd).sum((1, 2, 3))], -1).contiguous()
+    sums = torch.zeros(n, c, 3, dtype=torch.float64, device="cuda")
+    be.gn_bwd_reduce_gn(ga, y, (stats, gamma, beta, scale, vox, 8, 1e-5), sums)
+    # fp64 statement with the SAME fp32 coefficients the kernel derives (mask decisions at y*A + B > 0)
+    cpg = c // 8
+    sg = stats.view(n, 8, cpg, 2).sum(2)
+    m = cpg * vox
+    mean = sg[..., 0] / m
+    rstd = 1.0 / torch.sqrt((sg[..., 1] / m - mean * mean).clamp_min(0) + 1e-5)
+    mean_c, rstd_c = mean.repeat_interleave(cpg, 1), rstd.repeat_interleave(cpg, 1)
+    A = (rstd_c * gamma.double() * scale.double()).float()
+    B = ((beta.double() - mean_c * rstd_c * gamma.double()) * scale.double()).float()
+    mask = (torch.addcmul(B[:, None, None, None, :], y.float(), A[:, None, None, None, :]) > 0).double()
+    gm = ga.double() * mask
+    ref = torch.stack([gm.sum((1, 2, 3)), (gm * yd).sum((1, 2, 3)), yd.sum((1, 2, 3))], -1)
+    torch.cuda.synchronize()
+    den = ref.abs().amax(dim=(0, 1), keepdim=True) + 1e-9
+    assert ((sums - ref).abs() / den).max() < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_multi_tensor_pack_and_unpack(be, dtype):
     """b200seg_pack_weights_multi / b200seg_unpack_wgrads_multi (tap-contiguous smem-transposed paths and the
     generic path) against the single-tensor entry points, for every operand layout the engine requests."""

@@ -106,6 +106,51 @@ def test_tc_conv_large_volume_many_tiles(be):
     assert torch.equal(y2, y_c)
 
 
+@pytest.mark.parametrize("kind,n,sp,cin,cout", [
+    (K3, 2, (6, 6, 6), 256, 256),         # VNet3d bottom level: 6 voxel tiles, 108 k-blocks -> 6 ranges of 18
+    (K3, 1, (3, 5, 7), 256, 256),         # ragged, one sample
+    (K3, 2, (12, 12, 12), 128, 64),
+    (DOWN, 2, (6, 6, 6), 128, 256),       # 2x2x2 stride 2: 16 k-blocks
+    (K3, 3, (4, 4, 4), 64, 256),          # three samples: statistics flushed per sample by the finishing CTAs only
+])
+def test_tc_conv_split_k_equals_unsplit(be, monkeypatch, kind, n, sp, cin, cout):
+    """deep levels cut the (tap, channel-block) loop over several CTAs (conv_tc.cu: ksplit): same result as the
+    unsplit kernel up to fp32 summation order (bf16 outputs differ by at most one rounding), independent of
+    which range finishes last (bit-identical across launches), counters left clean for the next launch."""
+    g = torch.Generator().manual_seed(31)
+    dt = torch.bfloat16
+    k = 3 if kind == K3 else 2
+    w = torch.randn((cout, cin) + (k,) * 3, generator=g) * (2.0 / (cin * k ** 3)) ** 0.5
+    isp = sp if kind == K3 else tuple(2 * v for v in sp)
+    x = torch.randn((n,) + isp + (cin,), generator=g).to(dt).cuda()
+    bias = (torch.randn(cout, generator=g) * 0.1).cuda()
+    add = torch.randn((n,) + sp + (cout,), generator=g).to(dt).cuda()
+    wp = be.pack_weight(w.cuda(), kind, "fwd", dt, 3)
+    assert wp.code == 2
+
+    def run():
+        y = torch.zeros((n,) + sp + (cout,), dtype=dt, device="cuda")
+        st = torch.zeros(n, cout, 2, dtype=torch.float64, device="cuda")
+        be.conv(kind, 3, x, wp, bias, y, st, add)
+        torch.cuda.synchronize()
+        return y, st
+
+    monkeypatch.setenv("B200SEG_TC_KSPLIT", "0")
+    y0, st0 = run()
+    monkeypatch.delenv("B200SEG_TC_KSPLIT")
+    y1, st1 = run()
+    d = (y1.float() - y0.float()).abs()
+    assert float((d / (y0.float().abs() + 1e-2)).max()) < 1.0 / 64, "more than one bf16 rounding apart"
+    assert rel(y1, y0) < 1e-3 and rel(st1, st0) < 1e-5
+    for _ in range(12):                   # back-to-back launches reuse the slabs and the counters
+        y2, st2 = run()
+        assert torch.equal(y2, y1)
+        assert rel(st2, st1) < 1e-12
+    monkeypatch.setenv("B200SEG_TC_KSPLIT", "3")
+    y3, _ = run()
+    assert rel(y3, y0) < 1e-3
+
+
 WG_CASES = [
     # kind, dims, n, spatial, ka (x channels), kb (dy channels)
     (K3, 3, 1, (8, 8, 16), 16, 16),
