@@ -98,7 +98,7 @@ def load_library(path: Optional[str] = None):
     with _lib_lock:
         if _lib is not None and path is None:
             return _lib
-        p = path or LIB_PATH
+        p = path or os.environ.get("B200SEG_LIB") or LIB_PATH      # B200SEG_LIB: an alternative build (A/B timing)
         if not os.path.exists(p):
             raise RuntimeError(
                 f"{p} not found: build it with `python -m pytorchdeeplearing_b200.build` "

@@ -157,6 +157,17 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #define PDL_ENTER() b200seg::pdl_enter()
+// Split form for kernels with an on-chip prologue (mbarrier init, TMEM allocation, shared-memory clears): trigger
+// first, run the prologue, THEN wait -- the prologue overlaps the tail of the kernel before.  Nothing before
+// PDL_WAIT() may touch global memory: a chain of triggered kernels can be resident before ANY of them has completed,
+// so not even data written many launches ago (packed weights) is safe to read early.  Every thread executes the wait.
+#ifdef B200SEG_PDL_WAIT_FIRST      // A/B builds: wait before the prologue, as PDL_ENTER does
+#define PDL_TRIGGER() b200seg::pdl_enter()
+#define PDL_WAIT() ((void)0)
+#else
+#define PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 
 inline bool pdl_enabled() {
   static const bool on = [] {

@@ -437,7 +437,7 @@ constexpr int kHaloDepth = 6;          // cp.async groups (slices) in flight per
 
 template <int CIN, int COUT, int NCTA, bool BWD>
 __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const HaloArgs p) {
-  PDL_ENTER();
+  PDL_TRIGGER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   constexpr int KD = 3;
@@ -477,22 +477,10 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  // resident weights: 16-byte granules of the packed image [tap = (kd,kh,kw)][plane][co] -> [(kh,kw)][plane][2-kd][co]
-  for (uint32_t g = threadIdx.x; g < W_BYTES / 16u; g += blockDim.x) {
-    const uint32_t co = g % COUT;
-    const uint32_t t1 = g / COUT;
-    const uint32_t plane = t1 % CP;
-    const uint32_t tap = t1 / CP;
-    const uint32_t kd = tap / 9u, t9 = tap - kd * 9u;
-    const uint32_t dst = ((t9 * CP + plane) * 3u + (2u - kd)) * COUT + co;
-    *reinterpret_cast<uint4*>(s_w + dst * 16u) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + g * 16u);
-  }
   for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
   float* s_bias = s_stat + 8 * COUT;
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
   float* s_ab = s_bias + COUT;                                       // [2][Cout]: A, B of the sample being processed
   double* s_gd = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_ab + 2 * COUT) + 7) & ~(uintptr_t)7);   // [2][Cout] + [8][2]
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -504,6 +492,20 @@ __global__ void __launch_bounds__(kH3Threads, NCTA) conv_halo3_kernel(const Halo
     for (int c = 0; c < R * COUT; c += 16) tmem_st16_zero(trow + (uint32_t)c);
     tc_fence_before();
   }
+  // everything above is on-chip set-up and runs under the tail of the previous kernel; global memory from here on
+  PDL_WAIT();
+  // resident weights: 16-byte granules of the packed image [tap = (kd,kh,kw)][plane][co] -> [(kh,kw)][plane][2-kd][co]
+  for (uint32_t g = threadIdx.x; g < W_BYTES / 16u; g += blockDim.x) {
+    const uint32_t co = g % COUT;
+    const uint32_t t1 = g / COUT;
+    const uint32_t plane = t1 % CP;
+    const uint32_t tap = t1 / CP;
+    const uint32_t kd = tap / 9u, t9 = tap - kd * 9u;
+    const uint32_t dst = ((t9 * CP + plane) * 3u + (2u - kd)) * COUT + co;
+    *reinterpret_cast<uint4*>(s_w + dst * 16u) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w) + g * 16u);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+  fence_proxy_async();
   __syncthreads();
   tc_fence_after();
   constexpr int pd = 1;

@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t ws_nosw_desc(uint32_t lbo_bytes, uint32_t sb
 
 template <int CIN, int NT, int NACC, bool BWD>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWsArgs p) {
-  PDL_ENTER();
+  PDL_TRIGGER();
   constexpr int CP = CIN / 8;                                // 8-channel planes
   constexpr uint32_t PLANE = WS_PH * WS_PW * 16u;            // bytes of one plane of one slice
   constexpr uint32_t SLICE = (uint32_t)CP * PLANE;
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_halows_kernel(const HaloWs
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PDL_WAIT();               // barriers, TMEM and the statistics rows are set up under the tail of the previous kernel
   if (threadIdx.x == 0) ws_stamp(p, 1);
 
   // item -> (sample, column, first output slice, slices, channel group); the channel group is the fastest index

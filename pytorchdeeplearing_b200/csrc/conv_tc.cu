@@ -109,7 +109,7 @@ __device__ __forceinline__ int stat_col(int lane) {
 template <int BKC, int NCH>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
-  PDL_ENTER();
+  PDL_TRIGGER();
   constexpr uint32_t SWZ = BKC * 2;                 // bytes per smem row = swizzle span
   constexpr uint32_t A_BYTES = 128u * SWZ;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PDL_WAIT();               // everything above is on-chip set-up: it runs under the tail of the previous kernel
 
   if (warp == 0) {
     // ===================================================== TMA producer

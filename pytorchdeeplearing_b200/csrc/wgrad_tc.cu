@@ -36,7 +36,7 @@ constexpr int kWgMaxStages = 6;
 
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, const WgArgs p) {
-  PDL_ENTER();
+  PDL_TRIGGER();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t A_SUB = 128u * (uint32_t)p.CA * 2u;          // bytes of one A sub-tile
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PDL_WAIT();               // everything above is on-chip set-up: it runs under the tail of the previous kernel
   const bool has_work = tile_begin < tile_end && nmb > 0;
 
   if (warp == 0) {
