@@ -264,6 +264,22 @@ int b200seg_head_mask(const b200seg_tensor* x, const float* w, const float* bias
 int b200seg_mask_logits(const float* logits, int64_t nvox, int C, float threshold, uint8_t* mask, int device,
                         b200seg_stream stream);
 
+/* ---- device-side input staging: the per-sample host work of the reference's datasets, from the raw
+ * 8-bit images.  datasetModelSegwithopencv.__getitem__ (model/dataset.py:138-142): image = (image - image.mean()) /
+ * image.std() in float64 with the population std, then .float(); labels .long() (dataset.py:150-157) with the trainer's
+ * y[y != 0] = 1 (model/modelUnet.py:130) when `binarize`.
+ *   b200seg_stage_u8_sums      sums[n][2] (ZEROED by the caller) += { sum x, sum x*x } of sample n, exact integers
+ *   b200seg_stage_u8_normalize out[n][i] = (float)(((double)x - mean_n) / std_n), fp32 or bf16 (out_dtype); a constant
+ *                              image gives NaN, as numpy's 0/0 does
+ *   b200seg_stage_labels_u8    out[i] = binarize ? (lab[i] != 0) : lab[i], int64
+ * img: [n][per_sample] uint8, densely packed. */
+int b200seg_stage_u8_sums(const uint8_t* img, int n, int64_t per_sample, uint64_t* sums, int device,
+                          b200seg_stream stream);
+int b200seg_stage_u8_normalize(const uint8_t* img, int n, int64_t per_sample, const uint64_t* sums, void* out,
+                               int out_dtype, int device, b200seg_stream stream);
+int b200seg_stage_labels_u8(const uint8_t* lab, int64_t count, int binarize, int64_t* out, int device,
+                            b200seg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

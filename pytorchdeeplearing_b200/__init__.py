@@ -19,10 +19,11 @@ from .graphed import GraphedStep
 from .optim import FusedAdamW, FusedAdam
 from .metric import dice_coeff, iou_coeff, multiclass_dice_coeff, multiclass_iou_coeff
 from .inference import predict, predict_mask, sliding_window_mask
+from .staging import InputStager, stage_batch
 
 __all__ = ["VNet3d", "VNet2d", "UNet3d", "UNet2d", "initialize_weights", "FusedAdamW", "FusedAdam", "dice_coeff",
            "iou_coeff", "multiclass_dice_coeff", "multiclass_iou_coeff", "predict", "predict_mask",
-           "sliding_window_mask", "set_precision", "get_precision",
+           "sliding_window_mask", "InputStager", "stage_batch", "set_precision", "get_precision",
            "enable_data_parallel", "disable_data_parallel", "install", "uninstall", "GraphedStep",
            "BinaryDiceLoss", "BinaryCrossEntropyLoss", "BinaryFocalLoss", "BinaryCrossEntropyDiceLoss",
            "BinaryDiceFocalLoss", "MutilCrossEntropyLoss", "MutilFocalLoss", "MutilDiceLoss",

@@ -83,6 +83,9 @@ _SIGNATURES = {
     "b200seg_dropout_masks": ([_vp, _vp, _i, _i, C.c_double, _vp, _i, _vp], C.c_int),
     "b200seg_head_mask": ([_PT, _vp, _vp, _vp, _i, _f, _i, _vp], C.c_int),
     "b200seg_mask_logits": ([_vp, _i64, _i, _f, _vp, _i, _vp], C.c_int),
+    "b200seg_stage_u8_sums": ([_vp, _i, _i64, _vp, _i, _vp], C.c_int),
+    "b200seg_stage_u8_normalize": ([_vp, _i, _i64, _vp, _vp, _i, _i, _vp], C.c_int),
+    "b200seg_stage_labels_u8": ([_vp, _i64, _i, _vp, _i, _vp], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
@@ -567,6 +570,28 @@ class CudaBackend:
         self._check(self.lib.b200seg_head_mask(C.byref(dx), w.data_ptr(), _p(bias), mask.data_ptr(), nc, threshold,
                                                dev, st))
         return True
+
+    # ------------------------------------------------------------------ input staging
+    def stage_images_u8(self, img, out):
+        """out[n] = (img[n] - mean_n) / std_n  (float64 arithmetic, population std; model/dataset.py:141-142) for a
+        dense uint8 batch ``img`` [N, ...]; ``out`` fp32 or bf16 with the same number of elements."""
+        dev, st = self._ds(img)
+        assert img.dtype == torch.uint8 and img.is_contiguous() and out.is_contiguous() and out.numel() == img.numel()
+        n = img.shape[0]
+        per = img.numel() // n
+        sums = torch.zeros((n, 2), dtype=torch.int64, device=img.device)      # uint64 bit patterns
+        self._check(self.lib.b200seg_stage_u8_sums(img.data_ptr(), n, per, sums.data_ptr(), dev, st))
+        self._check(self.lib.b200seg_stage_u8_normalize(img.data_ptr(), n, per, sums.data_ptr(), out.data_ptr(),
+                                                        _dt(out), dev, st))
+        return out
+
+    def stage_labels_u8(self, lab, out, binarize=True):
+        """out = lab.long(), with y[y != 0] = 1 (model/modelUnet.py:130) when ``binarize``"""
+        dev, st = self._ds(lab)
+        assert lab.dtype == torch.uint8 and out.dtype == torch.int64 and lab.is_contiguous() and out.is_contiguous()
+        self._check(self.lib.b200seg_stage_labels_u8(lab.data_ptr(), lab.numel(), 1 if binarize else 0, out.data_ptr(),
+                                                     dev, st))
+        return out
 
     def mask_logits(self, logits, threshold, mask):
         dev, st = self._ds(logits)

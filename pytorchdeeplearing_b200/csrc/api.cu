@@ -115,6 +115,10 @@ int dropout_masks(const long long* rng, const int* table, int nmasks, int total,
 int head_mask(const b200seg_tensor* x, const float* w, const float* bias, unsigned char* mask, int nc, float thr,
               int device, cudaStream_t st);
 int mask_logits(const float* logits, long long nv, int C, float thr, unsigned char* mask, int device, cudaStream_t st);
+int stage_u8_sums(const unsigned char* img, int n, long long per, unsigned long long* sums, int device, cudaStream_t st);
+int stage_u8_normalize(const unsigned char* img, int n, long long per, const unsigned long long* sums, void* out,
+                       int out_dtype, int device, cudaStream_t st);
+int stage_labels_u8(const unsigned char* lab, long long count, int binarize, long long* out, int device, cudaStream_t st);
 int loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f, float* loss,
                   float* lcoef, cudaStream_t s);
 int loss_bwd(const float* logits, const void* labels, int label_dtype, long long nvox_, int C, const float* lcoef,
@@ -499,6 +503,31 @@ int b200seg_mask_logits(const float* logits, int64_t nvox_, int C, float thresho
   B200_CHECK_ARG(logits && mask && nvox_ > 0 && C > 0, "b200seg_mask_logits: bad argument");
   B200_DEVICE(device);
   return mask_logits(logits, nvox_, C, threshold, mask, device, ST(stream));
+}
+
+int b200seg_stage_u8_sums(const uint8_t* img, int n, int64_t per_sample, uint64_t* sums, int device,
+                          b200seg_stream stream) {
+  B200_CHECK_ARG(img && sums && n > 0 && per_sample > 0, "b200seg_stage_u8_sums: bad argument");
+  B200_CHECK_ARG(n <= 65535, "b200seg_stage_u8_sums: at most 65535 samples per call (got %d)", n);
+  B200_DEVICE(device);
+  return stage_u8_sums(img, n, per_sample, reinterpret_cast<unsigned long long*>(sums), device, ST(stream));
+}
+
+int b200seg_stage_u8_normalize(const uint8_t* img, int n, int64_t per_sample, const uint64_t* sums, void* out,
+                               int out_dtype, int device, b200seg_stream stream) {
+  B200_CHECK_ARG(img && sums && out && n > 0 && per_sample > 0, "b200seg_stage_u8_normalize: bad argument");
+  B200_CHECK_ARG(n <= 65535, "b200seg_stage_u8_normalize: at most 65535 samples per call (got %d)", n);
+  B200_CHECK_ARG(out_dtype == B200SEG_F32 || out_dtype == B200SEG_BF16, "b200seg_stage_u8_normalize: fp32 or bf16 output");
+  B200_DEVICE(device);
+  return stage_u8_normalize(img, n, per_sample, reinterpret_cast<const unsigned long long*>(sums), out, out_dtype,
+                            device, ST(stream));
+}
+
+int b200seg_stage_labels_u8(const uint8_t* lab, int64_t count, int binarize, int64_t* out, int device,
+                            b200seg_stream stream) {
+  B200_CHECK_ARG(lab && out && count > 0, "b200seg_stage_labels_u8: bad argument");
+  B200_DEVICE(device);
+  return stage_labels_u8(lab, count, binarize, reinterpret_cast<long long*>(out), device, ST(stream));
 }
 
 int b200seg_loss_finalize(const double* part, int C, int terms, const float* alpha, float gamma, float alpha_f,

@@ -358,6 +358,18 @@ class EmuBackend:
         self.mask_logits(z, threshold, mask)
         return True
 
+    def stage_images_u8(self, img, out):
+        a = img.double()
+        dims = tuple(range(1, a.dim()))
+        mean = a.mean(dims, keepdim=True)
+        sd = ((a - mean) ** 2).mean(dims, keepdim=True).sqrt()
+        out.copy_(((a - mean) / sd).float().reshape(out.shape).to(out.dtype))
+        return out
+
+    def stage_labels_u8(self, lab, out, binarize=True):
+        out.copy_(((lab != 0).long() if binarize else lab.long()).reshape(out.shape))
+        return out
+
     def mask_logits(self, logits, threshold, mask):
         if logits.shape[-1] == 1:
             mask.copy_(((torch.sigmoid(logits[..., 0]) > threshold) * 255).to(torch.uint8).reshape(mask.shape))

@@ -394,3 +394,39 @@ def test_graphed_step_with_optimizer_updates_weights(fused):
         d = (p.detach() - sdg[n].detach()).abs().flatten()
         assert d.mean() < 3e-5 and d.kthvalue(max(1, int(0.99 * d.numel()))).values < 3e-4, (n, d.mean().item())
     assert abs(step.dice.item() - b200.multiclass_dice_coeff(torch.softmax(lo, 1), y).item()) < 1e-6
+
+
+def test_input_stager_host_logic_on_the_emulated_backend():
+    """InputStager (staging.py): slot rotation, shape/dtype checks, label handling -- arithmetic by the emulated ops,
+    checked against the oracle restatement of model/dataset.py:138-157"""
+    import numpy as np
+    from oracle import staging as ostaging
+    from pytorchdeeplearing_b200.staging import InputStager, stage_batch
+    rng = np.random.default_rng(3)
+    st = InputStager("cpu", (3, 16, 24), backend=EmuBackend())
+    batches = [(rng.integers(0, 256, (3, 16, 24), dtype=np.uint8), (rng.random((3, 16, 24)) > 0.6).astype(np.uint8) * 255)
+               for _ in range(5)]
+    st.put(*batches[0])
+    st.put(*batches[1])
+    with pytest.raises(RuntimeError):
+        st.put(*batches[2])                       # both slots hold untaken batches
+    for i in range(5):
+        x, y = st.get()
+        assert x.shape == (3, 1, 16, 24) and x.dtype == torch.float32 and y.dtype == torch.int64
+        assert (x - ostaging.zscore_u8(batches[i][0])).abs().max() < 1e-6
+        assert torch.equal(y, ostaging.labels_from_u8(batches[i][1]))
+        st.release()
+        if i + 2 < 5:
+            st.put(*batches[i + 2])
+    with pytest.raises(RuntimeError):
+        st.get()
+    with pytest.raises(ValueError):
+        st.put(batches[0][0].astype(np.float32))
+    with pytest.raises(ValueError):
+        st.put(batches[0][0][:2])
+    st.put(batches[0][0])                         # images only
+    x, y = st.get()
+    assert y is None
+    x2, y2 = stage_batch(torch.from_numpy(batches[1][0]), torch.from_numpy(batches[1][1]), binarize_labels=False,
+                         backend=EmuBackend())
+    assert torch.equal(y2, torch.from_numpy(batches[1][1]).long()) and (x2 - ostaging.zscore_u8(batches[1][0])).abs().max() < 1e-6

@@ -432,3 +432,57 @@ def test_metric_functions_on_device():
     # channels-last-strided probabilities (what the drop-in networks return) give the same number
     pcl = pm.cuda().permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
     assert abs(b200.multiclass_dice_coeff(pcl, tm.cuda()).item() - got) < 1e-7
+
+
+def test_input_staging_kernels_match_reference_dataset_outputs():
+    """csrc/staging.cu through the C ABI against tests/golden/staging.npz (outputs of the reference's own
+    datasetModelSegwithopencv + the trainer's label binarisation) and against the oracle restatement on larger,
+    unaligned and constant images.  Tolerance: 2 ulp of fp32 relative to max(|x|, 1) (the kernel's mean and variance
+    are exact integers, numpy rounds its float64 variance a few more times); labels bit-exact."""
+    import os
+    import numpy as np
+    from oracle import staging as ostaging
+    from pytorchdeeplearing_b200.staging import InputStager, stage_batch
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "staging.npz"))
+    img = torch.from_numpy(gold["images_u8"]).cuda()
+    lab = torch.from_numpy(gold["labels_u8"]).cuda()
+    x, y = stage_batch(img, lab)
+    ref = torch.from_numpy(gold["x"]).cuda()
+    assert x.shape == ref.shape and x.dtype == torch.float32
+    assert ((x - ref).abs() / ref.abs().clamp_min(1.0)).max() < 2.5e-7
+    assert torch.equal(y.cpu(), torch.from_numpy(gold["y"]))
+    rng = np.random.default_rng(11)
+    for shape in ((8, 512, 512), (3, 37, 53), (2, 5, 96, 96), (1, 1, 17)):
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        if shape[0] > 1:
+            a[1] = (rng.normal(200, 1.5, shape[1:]).clip(0, 255)).astype(np.uint8)       # low variance, large mean
+        b = (rng.integers(0, 4, shape, dtype=np.uint8))
+        x, y = stage_batch(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+        ref = ostaging.zscore_u8(a).cuda()
+        assert ((x - ref).abs() / ref.abs().clamp_min(1.0)).max() < 2.5e-7, shape
+        assert torch.equal(y.cpu(), ostaging.labels_from_u8(b))
+        _, y_raw = stage_batch(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), binarize_labels=False)
+        assert torch.equal(y_raw.cpu(), torch.from_numpy(b).long())
+        xb, _ = stage_batch(torch.from_numpy(a).cuda(), dtype=torch.bfloat16)
+        assert torch.equal(xb, x.to(torch.bfloat16))
+    const = np.full((2, 32, 32), 9, np.uint8)
+    xc, _ = stage_batch(torch.from_numpy(const).cuda())
+    assert bool(torch.isnan(xc).all())            # numpy: 0/0 -> nan for a constant image
+    # double-buffered host -> device path, consumed by a training step
+    st = InputStager("cuda", (2, 64, 64))
+    net = b200.UNet2d(1, 1).cuda()
+    lossfn = b200.BinaryDiceLoss()
+    batches = [(rng.integers(0, 256, (2, 64, 64), dtype=np.uint8), (rng.random((2, 64, 64)) > 0.7).astype(np.uint8) * 255)
+               for _ in range(4)]
+    st.put(*batches[0])
+    for i in range(4):
+        if i + 1 < 4:
+            st.put(*batches[i + 1])
+        x, y = st.get()
+        assert ((x.cpu() - ostaging.zscore_u8(batches[i][0])).abs()).max() < 1e-6
+        assert torch.equal(y.cpu(), ostaging.labels_from_u8(batches[i][1]))
+        logits, _ = net(x)
+        loss = lossfn(logits, y)
+        loss.backward()
+        st.release()
+        assert torch.isfinite(loss.detach()).item()

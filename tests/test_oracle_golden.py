@@ -125,3 +125,15 @@ def test_loss_matches_reference(key, name, which, gamma):
     assert abs(v.item() - float(gold[key + "_value"])) < 3e-6
     ref = torch.from_numpy(gold[key + "_grad"])
     assert (z.grad - ref).abs().max() < 1e-8 + 1e-4 * ref.abs().max()
+
+
+def test_input_staging_restatement_equals_reference_dataset():
+    """oracle/staging.py against what the reference's datasetModelSegwithopencv returned for the same 8-bit files
+    (tests/golden/make_golden_staging.py): bit-equal images, equal labels"""
+    from oracle import staging
+    gold = _load("staging")
+    x = staging.zscore_u8(gold["images_u8"])
+    assert x.dtype == torch.float32 and tuple(x.shape) == gold["x"].shape
+    assert torch.equal(x, torch.from_numpy(gold["x"]))
+    y = staging.labels_from_u8(gold["labels_u8"])
+    assert y.dtype == torch.int64 and torch.equal(y, torch.from_numpy(gold["y"]))

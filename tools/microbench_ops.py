@@ -192,6 +192,26 @@ def bench_conv(be, tm, n):
                bytes_=(n * s ** 3 * ci + vo * co) * 2, flops=2 * vo * taps * ci * co)
 
 
+def bench_convbwd(be, tm, n):
+    """data-gradient conv with the GroupNorm-backward sums of the producer layer in its epilogue (b200seg_conv_bwdstats)"""
+    for (c, s) in ((32, 48), (64, 24), (128, 12)):
+        w = rnd((c, c, 3, 3, 3), torch.float32, 0.05)
+        wp = be.pack_weight(w, K3, "dgrad", torch.bfloat16, 3, vox=s ** 3)
+        dy, yfwd, add = rnd((n, s, s, s, c)), rnd((n, s, s, s, c)), rnd((n, s, s, s, c))
+        g = torch.empty_like(dy)
+        yf = yfwd.float()
+        stats = torch.stack([yf.sum(dim=(1, 2, 3)).double(), (yf * yf).sum(dim=(1, 2, 3)).double()], -1).contiguous()
+        gamma, beta = rnd((c,), torch.float32) + 1.0, rnd((c,), torch.float32, 0.1)
+        scale = torch.full((n, c), 1.25, dtype=torch.float32, device=DEV)
+        gn = (stats, gamma, beta, scale, s ** 3, 8, 1e-5)
+        sums = torch.zeros((n, c, 3), dtype=torch.float64, device=DEV)
+        vo = n * s ** 3
+        if not be.conv_bwdstats_ok(K3, 3, dy, wp, g, add, yfwd):
+            continue
+        tm.run(f"conv+gn_bwd_sums {c}->{c} @{s}^3", lambda: be.conv_bwdstats(K3, 3, dy, wp, g, add, yfwd, gn, sums),
+               bytes_=vo * c * 2 * 4, flops=2 * vo * 27 * c * c)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=7)
@@ -214,6 +234,8 @@ def main():
             bench_wgrad(be, tm, a.batch)
         if "conv" in which:
             bench_conv(be, tm, a.batch)
+        if "convbwd" in which:
+            bench_convbwd(be, tm, a.batch)
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/microbench_{a.tag}.json", "w") as f:
         json.dump({"env": {k: v for k, v in os.environ.items() if k.startswith("B200SEG_")}, "rows": tm.rows}, f, indent=1)
