@@ -258,9 +258,10 @@ class CudaBackend:
                                                      s_t, s_k, s_n2, s_n1, flip, dev, st))
         return PackedWeight(out, code, w, kind, which, dims)
 
-    def _table_to_device(self, descs, device):
+    def _table_to_device(self, descs, device, stream=None):
         """ctypes descriptor array -> device tensor, written by a kernel that receives the bytes as ARGUMENTS (no
-        host-to-device memcpy: see b200seg_upload_table)."""
+        host-to-device memcpy: see b200seg_upload_table).  The tensor is allocated on the CURRENT stream; with
+        ``stream`` the writing kernel goes to that torch stream after it has waited for the current one."""
         arr = (PackDesc * len(descs))(*descs)
         nbytes = C.sizeof(arr)
         pad = (nbytes + 15) // 16 * 16
@@ -268,12 +269,17 @@ class CudaBackend:
         C.memmove(buf, arr, nbytes)
         devt = torch.empty(pad, dtype=torch.uint8, device=device)
         dev = device.index if device.index is not None else torch.cuda.current_device()
-        self._check(self.lib.b200seg_upload_table(C.cast(buf, C.c_void_p), pad, devt.data_ptr(), dev,
-                                                  torch.cuda.current_stream(dev).cuda_stream))
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(dev))
+        st = stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        self._check(self.lib.b200seg_upload_table(C.cast(buf, C.c_void_p), pad, devt.data_ptr(), dev, st))
         return devt
 
-    def pack_many(self, reqs):
-        """reqs: [(w, kind, which, dtype, dims, vox)] -> [PackedWeight]: ONE launch for all operands."""
+    def pack_many(self, reqs, stream=None):
+        """reqs: [(w, kind, which, dtype, dims, vox)] -> [PackedWeight]: ONE launch for all operands.
+        ``stream``: launch on that torch stream instead of the current one (the outputs are still allocated on the
+        current stream; the launch is ordered after everything the current stream has enqueued so far, and the CALLER
+        makes the consumer wait for ``stream``)."""
         if not reqs:
             return []
         dev, st = self._ds(reqs[0][0])
@@ -289,15 +295,18 @@ class CudaBackend:
                                       flip, blocks, nb))
                 blocks += nb
             outs.append(PackedWeight(out, code, w, kind, which, dims))
-        table = self._table_to_device(descs, reqs[0][0].device)
-        self._check(self.lib.b200seg_pack_weights_multi(table.data_ptr(), len(descs), blocks, dev, st))
+        # every allocation above and the table's are made on the current stream; only the two launches move
+        table = self._table_to_device(descs, reqs[0][0].device, stream)
+        self._check(self.lib.b200seg_pack_weights_multi(table.data_ptr(), len(descs), blocks, dev,
+                                                        stream.cuda_stream if stream is not None else st))
         self._keep_tables.append(table)
         if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
             self._keep_tables.pop(0)
         return outs
 
-    def unpack_many(self, items):
-        """items: [(dwp [t][k][n], grad view)] -> parameter-layout gradients, ONE launch."""
+    def unpack_many(self, items, stream=None):
+        """items: [(dwp [t][k][n], grad view)] -> parameter-layout gradients, ONE launch (on ``stream`` if given, after
+        it has waited for the current stream; see ``pack_many``)."""
         if not items:
             return
         dev, st = self._ds(items[0][0])
@@ -307,8 +316,9 @@ class CudaBackend:
             nb = max(1, min(256, (dwp.numel() + 4095) // 4096))
             descs.append(PackDesc(dwp.data_ptr(), grad.data_ptr(), 1, t, k * t, 0, F32, t, k, n, 1, 0, blocks, nb))
             blocks += nb
-        table = self._table_to_device(descs, items[0][0].device)
-        self._check(self.lib.b200seg_unpack_wgrads_multi(table.data_ptr(), len(descs), blocks, dev, st))
+        table = self._table_to_device(descs, items[0][0].device, stream)
+        self._check(self.lib.b200seg_unpack_wgrads_multi(table.data_ptr(), len(descs), blocks, dev,
+                                                         stream.cuda_stream if stream is not None else st))
         self._keep_tables.append(table)
         if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
             self._keep_tables.pop(0)

@@ -8,6 +8,8 @@
 // (model/metric.py:146-181 dice_coeff / iou_coeff / multiclass_dice_coeff on the thresholded probabilities), so the
 // training step needs no separate read of ``probs`` for it, and counts labels outside [0, C) (the reference raises
 // in F.one_hot / F.cross_entropy; here the count lands in ``part`` and the host raises).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200seg {
@@ -470,8 +472,15 @@ static int loss_blocks(long long nvox_, int device) {
 
 // blocks per sample for the (blocks, N) grids of the partial-sum kernels
 static dim3 sample_grid(long long vox, int N, int device) {
+  // blocks per SM over the whole grid: every block ends in one fp64 atomic per partial sum (15 for two classes) on
+  // the SAME few addresses, so more blocks buy load parallelism and pay in serialised atomics (B200SEG_LOSS_BPS: A/B)
+  static const int bps = [] {
+    const char* e = getenv("B200SEG_LOSS_BPS");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 16 ? v : 8;
+  }();
   long long per = (vox + 256 * 4 - 1) / (256 * 4);
-  long long cap = ((long long)num_sms(device) * 8 + N - 1) / N;
+  long long cap = ((long long)num_sms(device) * bps + N - 1) / N;
   if (per > cap) per = cap;
   if (per < 1) per = 1;
   return dim3((unsigned)per, (unsigned)N, 1);

@@ -59,6 +59,26 @@ def _taps(kind: int, dims: int) -> int:
     return 8 if dims == 3 else 4
 
 
+# B200SEG_OVERLAP: bit mask of host-side scheduling options that move work off the serial kernel chain of a step onto
+# the side stream (all of them launch the SAME kernels on the SAME data; only stream placement / launch grouping changes)
+OV_PACK = 1      # forward: only the operands of the first block(s) are packed on the main stream; the rest of the
+                 # step's pack launch runs on the side stream under the first convolutions
+OV_UNPACK = 2    # backward: the weight gradients finished by the time the deepest encoder block is done (96 % of the
+                 # bytes) are brought to parameter layout on the side stream there, not after the last kernel of the step
+OV_TAIL = 4      # backward: the weight gradient of the first input-block branch runs beside the GroupNorm backward of
+                 # the second one (neither has a data gradient behind it)
+OV_ZERO = 8      # the zero fills backward needs (gradient bucket, accumulator arenas) are issued on the side stream
+                 # during forward
+_OV_DEFAULT = "0"
+
+
+def overlap_mask() -> int:
+    try:
+        return int(os.environ.get("B200SEG_OVERLAP", _OV_DEFAULT))
+    except ValueError:
+        return 0
+
+
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
@@ -78,8 +98,9 @@ class _ZeroArena:
     """One zero-filled allocation per pass, handed out as views: replaces ~100 tiny fill launches per step
     (GroupNorm statistics, backward sums, split-K weight-gradient accumulators) by one memset each."""
 
-    def __init__(self, dtype: torch.dtype, numel: int, device):
-        self.buf = torch.zeros(max(1, numel), dtype=dtype, device=device)
+    def __init__(self, dtype: torch.dtype, numel: int, device, buf: Optional[Tensor] = None):
+        # ``buf``: an already zeroed (or being zeroed, on a stream the user joins) allocation of that size
+        self.buf = torch.zeros(max(1, numel), dtype=dtype, device=device) if buf is None else buf
         self.off = 0
 
     def take(self, shape) -> Tensor:
@@ -120,6 +141,9 @@ class Engine:
         self.mask_threshold: Optional[float] = None   # not None: inference head -> uint8 mask, no logits / probs
         self._side = None                      # side stream carrying this pass's weight gradients (if any)
         self._side_keep: List[object] = []     # operands of side-stream kernels stay referenced until the join
+        self._fwd_side = None                  # side stream carrying forward-time work (late pack, zero fills) not yet joined
+        self._late: set = set()                # weights whose forward operand comes from the side-stream pack
+        self._pre_bwd = None                   # (flat, z64 buffer, z32 buffer) zeroed during forward for backward
 
     # ---------------------------------------------------------------- allocation helpers
     def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
@@ -131,15 +155,38 @@ class Engine:
             return arena.take(tuple(shape))
         return torch.zeros(shape, dtype=dtype, device=device)
 
-    def _begin_pass(self, n: int, device, backward: bool) -> None:
+    def _arena_sizes(self, n: int, backward: bool) -> Tuple[int, int]:
         gn_ch = sum(p.numel() for k, p in self.P.items() if p.dim() == 1 and k.endswith(".weight"))
         per = 3 if backward else 2
-        self._z64 = _ZeroArena(torch.float64, n * gn_ch * per * 2 + 64 * 40, device)
+        wel = sum(p.numel() for p in self.P.values() if p.dim() > 1) if backward else 0
+        return n * gn_ch * per * 2 + 64 * 40, wel + 16 * 64
+
+    def _begin_pass(self, n: int, device, backward: bool) -> None:
+        n64, n32 = self._arena_sizes(n, backward)
+        pre = self._pre_bwd if backward else None
+        self._z64 = _ZeroArena(torch.float64, n64, device, buf=pre[1] if pre is not None else None)
         if backward:
-            wel = sum(p.numel() for p in self.P.values() if p.dim() > 1)
-            self._z32 = _ZeroArena(torch.float32, wel + 16 * 64, device)
+            self._z32 = _ZeroArena(torch.float32, n32, device, buf=pre[2] if pre is not None else None)
         else:
             self._z32 = None
+
+    def _zero_ahead(self, n: int, device) -> None:
+        """OV_ZERO: allocate what backward wants zero-filled (flat gradient bucket, both accumulator arenas) now and
+        fill it on the side stream, under the forward kernels; joined with the late pack (``_join_fwd_side``)."""
+        side = _side_stream(device)
+        if side is None:
+            return
+        n64, n32 = self._arena_sizes(n, True)
+        total = sum(p.numel() for p in self.P.values())
+        bufs = (torch.empty(total, dtype=torch.float32, device=device),
+                torch.empty(max(1, n64), dtype=torch.float64, device=device),
+                torch.empty(max(1, n32), dtype=torch.float32, device=device))
+        side.wait_stream(torch.cuda.current_stream(device))     # after the allocations: whoever held the blocks is done
+        with torch.cuda.stream(side):
+            for b in bufs:
+                b.zero_()
+        self._pre_bwd = bufs
+        self._fwd_side = side
 
     def _next_mask(self) -> Optional[Tensor]:
         if self.masks is None:
@@ -148,18 +195,56 @@ class Engine:
         self._mi += 1
         return m
 
-    def _prepack(self, specs, need_grad: bool) -> None:
+    def _prepack(self, specs, need_grad: bool, n_early: int = 0) -> None:
         """ONE launch packs every conv operand of the step (forward and data-gradient layouts).
-        specs: [(wname, kind, vox_out, vox_in, needs_dgrad)]."""
-        reqs, keys = [], []
+        specs: [(wname, kind, vox_out, vox_in, needs_dgrad)].  With OV_PACK the forward operands of the first
+        ``n_early`` specs are packed by a small launch on the main stream and everything else by a second launch on the
+        side stream, which the main stream joins at the first use of one of those operands."""
+        reqs, keys, late_reqs, late_keys = [], [], [], []
         self._tag(None)
-        for wname, kind, vox_out, vox_in, dgrad in specs:
-            reqs.append((self.P[wname], kind, "fwd", self.T, self.dims, vox_out))
-            keys.append((wname, "fwd"))
+        ov = overlap_mask()
+        split = bool(ov & OV_PACK) and 0 < n_early < len(specs)
+        for i, (wname, kind, vox_out, vox_in, dgrad) in enumerate(specs):
+            early = not split or i < n_early
+            (reqs if early else late_reqs).append((self.P[wname], kind, "fwd", self.T, self.dims, vox_out))
+            (keys if early else late_keys).append((wname, "fwd"))
             if need_grad and dgrad:
-                reqs.append((self.P[wname], kind, "dgrad", self.T, self.dims, vox_in))
-                keys.append((wname, "dgrad"))
+                (late_reqs if split else reqs).append((self.P[wname], kind, "dgrad", self.T, self.dims, vox_in))
+                (late_keys if split else keys).append((wname, "dgrad"))
         self._packs = dict(zip(keys, self.be.pack_many(reqs)))
+        self._late, self._fwd_side, self._pre_bwd = set(), None, None
+        dev = specs and self.P[specs[0][0]].device
+        if late_reqs:
+            side = _side_stream(dev)
+            if side is not None:
+                self._packs.update(zip(late_keys, self.be.pack_many(late_reqs, stream=side)))
+                self._late = {k[0] for k in late_keys if k[1] == "fwd"}
+                self._fwd_side = side
+            else:
+                self._packs.update(zip(late_keys, self.be.pack_many(late_reqs)))
+        if need_grad and (ov & OV_ZERO) and specs:
+            self._zero_ahead(self._batch, dev)
+
+    def _join_fwd_side(self) -> None:
+        """the main stream waits for the forward-time side work (late pack, zero fills)"""
+        if self._fwd_side is not None:
+            torch.cuda.current_stream(self._fwd_side.device).wait_stream(self._fwd_side)
+            self._fwd_side = None
+        self._late = set()
+
+    def _early_unpack(self) -> None:
+        """OV_UNPACK (single GPU; data parallel has ``_flush_bucket`` at the same place): the weight gradients
+        accumulated so far go to parameter layout on the side stream, in stream order behind the kernels that produced
+        them; the unpack at the end of backward only handles the remaining (small, full-resolution) layers."""
+        if not (overlap_mask() & OV_UNPACK) or self.bucket_hook is not None or not self._unpack_list:
+            return
+        items, self._unpack_list = self._unpack_list, []
+        side = self._side
+        if side is None:
+            self.be.unpack_many(items)
+            return
+        self.be.unpack_many(items, stream=side)     # the side stream first waits for the main stream's position
+        self._side_keep.append(items)
 
     def _join_side(self) -> None:
         if self._side is not None:
@@ -184,6 +269,7 @@ class Engine:
         self.be.unpack_many(self._unpack_list)
         self._unpack_list = []
         self._packs = {}
+        self._pre_bwd = None
 
     def _tag(self, wname: Optional[str]) -> None:
         """instrumentation hook: a profiling wrapper around the backend (bench.py) learns which network block
@@ -195,6 +281,8 @@ class Engine:
     def conv_raw(self, kind: int, wname: str, bname: Optional[str], x: Tensor, y: Tensor,
                  stats: Optional[Tensor] = None) -> None:
         w = self.P[wname]
+        if self._fwd_side is not None and wname in self._late:
+            self._join_fwd_side()
         wpk = self._packs.get((wname, "fwd"))
         if wpk is None:
             wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims, vox=y.numel() // (y.shape[0] * y.shape[-1]))
@@ -230,6 +318,7 @@ class Engine:
         """OutputTransition3d / UNet head: 1x1 conv to the classes + sigmoid/softmax (VNet3d.py:90-99).
         Inference form (``mask_threshold`` set; predict, model/modelVNet.py:655-676): the uint8 mask directly."""
         self._tag(wname)
+        self._join_fwd_side()                      # the last forward op: nothing of this pass stays un-joined
         if self.mask_threshold is not None:
             mask = torch.empty((x.shape[0],) + tuple(sp0), dtype=torch.uint8, device=x.device)
             if not self.be.head_mask(x, self.P[wname], self.P[bname], mask, float(self.mask_threshold)):
@@ -266,7 +355,8 @@ class Engine:
         return self.grads[name]
 
     def bwd_layer(self, L: Layer, g_act: Tensor, need_dx: bool, dx_out: Optional[Tensor] = None,
-                  dx_addend: Optional[Tensor] = None, prev: Optional[Layer] = None) -> Optional[Tensor]:
+                  dx_addend: Optional[Tensor] = None, prev: Optional[Layer] = None,
+                  side_wgrad: bool = False) -> Optional[Tensor]:
         """Backward of one conv(+GN/drop/ReLU) application.  ``g_act`` is the gradient w.r.t.
         the layer's activation output (or w.r.t. the raw conv output when the layer has no
         GroupNorm).  Returns the gradient w.r.t. the layer input (written to ``dx_out``).
@@ -318,7 +408,9 @@ class Engine:
         else:
             dwp = self.zeros((taps, cin, cout), torch.float32, dev)
             wg = (L.kind, self.dims, L.x, dy, dwp)
-        side = _side_stream(dev) if need_dx else None        # nothing to overlap with when there is no dgrad
+        # without a data gradient there is nothing to overlap with, unless the caller has more work for the main
+        # stream (``side_wgrad``: the other branch of the input block)
+        side = _side_stream(dev) if (need_dx or side_wgrad) else None
         if side is not None:
             # dW only feeds the final unpack: run it beside the dgrad -> next-layer chain
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -352,7 +444,10 @@ class Engine:
         """One flat fp32 bucket; ``self.grads`` are views in state_dict order (the bucket is
         what the data-parallel all-reduce sums)."""
         total = sum(p.numel() for p in self.P.values())
-        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        if self._pre_bwd is not None and self._pre_bwd[0].numel() == total:
+            flat = self._pre_bwd[0]                       # zeroed on the side stream during forward (OV_ZERO)
+        else:
+            flat = torch.zeros(total, dtype=torch.float32, device=device)
         off = 0
         self.grads, self._goff, self._flat = {}, {}, flat
         for name, p in self.P.items():
@@ -408,7 +503,8 @@ class Engine:
             specs.append((name + ".up_conv.weight", UP, vox[i], vox[i + 1], True))
             specs.append((name + ".conv.weight", K1, vox[i], vox[i], True))
             specs += [(f"{name}.ops.{j}.conv1.weight", K3, vox[i], vox[i], True) for j in range(nops)]
-        self._prepack(specs, need_grad)
+        self._batch = n
+        self._prepack(specs, need_grad, n_early=5)         # in_tr (2) + down_tr32 (down conv + 2 ops)
 
         # ---- InputTransition3d (VNet3d.py:34-43): one bn1 serves both branches
         La = self.conv_gn(K3, "in_tr.conv1.weight", "in_tr.conv1.bias", "in_tr.bn1", xin, sp0, f)
@@ -491,8 +587,9 @@ class Engine:
             g = self.bwd_layer(Ld, gh, True, dx_addend=gskip[i])
             if i == 3:
                 self._flush_bucket("down_tr256.down_conv.weight")
+                self._early_unpack()
         La, Lb = sv["in_tr"]
-        self.bwd_layer(La, g, False)
+        self.bwd_layer(La, g, False, side_wgrad=bool(overlap_mask() & OV_TAIL))
         self.bwd_layer(Lb, g, False)
         self._finish_backward()
         return flat
@@ -533,7 +630,8 @@ class Engine:
             specs.append((f"upconv{i + 1}.weight", UP, vox[i], vox[i + 1], True))
             specs.append((f"decoder{i + 1}.dec{i + 1}conv1.weight", K3, vox[i], vox[i], True))
             specs.append((f"decoder{i + 1}.dec{i + 1}conv2.weight", K3, vox[i], vox[i], True))
-        self._prepack(specs, need_grad)
+        self._batch = n
+        self._prepack(specs, need_grad, n_early=2)         # encoder1
 
         def block(mod: str, name: str, h: Tensor, sp, co: int, dst: Tensor):
             L1 = self.conv_gn(K3, f"{mod}.{name}conv1.weight", None, f"{mod}.{name}norm1", h, sp, co)
@@ -580,6 +678,7 @@ class Engine:
         L1, L2 = sv["bottleneck"]
         g = self.bwd_layer(L1, self.bwd_layer(L2, g, True, prev=L1), True)
         self._flush_bucket("bottleneck.bottleneckconv1.weight")
+        self._early_unpack()
         for i in (3, 2, 1, 0):
             e, pooled = sv[f"pool{i + 1}"]
             ge = torch.empty(e.shape, dtype=self.T, device=e.device)

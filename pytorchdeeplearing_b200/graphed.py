@@ -63,6 +63,9 @@ class GraphedStep:
         self._terms, self._alpha, self._gamma, self._alpha_f = loss_spec(lossfn)
         dev = self.x.device
         self._one = torch.ones(1, dtype=torch.float32, device=dev)
+        # class weights of the loss: a constant of the step, created once (not a fill launch inside every step)
+        self._alpha_t = torch.ones(c, dtype=torch.float32, device=dev) if self._alpha is None else \
+            torch.as_tensor(self._alpha, dtype=torch.float32, device=dev)
         self._fused_opt = optimizer is not None and _is_fused_optimizer(optimizer)
         if self._fused_opt:
             optimizer.prepare()
@@ -132,10 +135,7 @@ class GraphedStep:
         dev = z.device
         loss = torch.empty((), dtype=torch.float32, device=dev)
         lcoef = torch.empty(2 * c + 3 if c > 1 else 5, dtype=torch.float32, device=dev)
-        alpha = self._alpha
-        alpha = torch.ones(c, dtype=torch.float32, device=dev) if alpha is None else \
-            torch.as_tensor(alpha, dtype=torch.float32, device=dev)
-        be.loss_finalize(part, c, self._terms, alpha, self._gamma, self._alpha_f, loss, lcoef)
+        be.loss_finalize(part, c, self._terms, self._alpha_t, self._gamma, self._alpha_f, loss, lcoef)
         dz = torch.empty_like(z)
         be.loss_bwd(z, self.y, lcoef, self._one, dz)
         g = dz if dz.dim() == 5 else dz.unsqueeze(1)

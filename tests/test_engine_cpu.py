@@ -430,3 +430,42 @@ def test_input_stager_host_logic_on_the_emulated_backend():
     x2, y2 = stage_batch(torch.from_numpy(batches[1][0]), torch.from_numpy(batches[1][1]), binarize_labels=False,
                          backend=EmuBackend())
     assert torch.equal(y2, torch.from_numpy(batches[1][1]).long()) and (x2 - ostaging.zscore_u8(batches[1][0])).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("kind,cin,ncls,spatial,lossname,losscls", [
+    ("vnet3d", 1, 2, (16, 16, 16), "MutilDiceLoss", b200.MutilDiceLoss),
+    ("unet2d", 1, 1, (32, 32), "BinaryDiceFocalLoss", b200.BinaryDiceFocalLoss),
+])
+def test_overlap_options_change_launch_grouping_not_results(kind, cin, ncls, spatial, lossname, losscls, monkeypatch):
+    """B200SEG_OVERLAP only regroups launches (two pack launches, an early unpack) and moves them between streams; on
+    the emulated backend (no streams) every mask must give bit-identical logits, loss and gradients."""
+    from pytorchdeeplearing_b200 import engine
+    spec, sd, model, ofwd, draw = _build(kind, cin, ncls, seed=9)
+    x, y = oracle.make_inputs(2, cin, spatial, ncls, seed=21)
+    torch.manual_seed(4)
+    model.train()
+    model.dropout_masks = draw(2)
+    lossfn = losscls(torch.ones(ncls)) if lossname.startswith("Mutil") else losscls()
+    be = runtime._TEST_BACKEND
+    calls = {"pack": 0, "unpack": 0}
+    pack0, unpack0 = be.pack_many, be.unpack_many
+    monkeypatch.setattr(be, "pack_many", lambda reqs: (calls.__setitem__("pack", calls["pack"] + 1), pack0(reqs))[1])
+    monkeypatch.setattr(be, "unpack_many",
+                        lambda items: (calls.__setitem__("unpack", calls["unpack"] + 1), unpack0(items))[1])
+    results = {}
+    for mask in (0, 15):
+        monkeypatch.setenv("B200SEG_OVERLAP", str(mask))
+        assert engine.overlap_mask() == mask
+        calls["pack"] = calls["unpack"] = 0
+        for p in model.parameters():
+            p.grad = None
+        logits, _ = model(x)
+        loss = lossfn(logits, y)
+        loss.backward()
+        results[mask] = (logits.detach().clone(), loss.detach().clone(),
+                         [p.grad.clone() for p in model.parameters()], dict(calls))
+    assert results[0][3] == {"pack": 1, "unpack": 1}
+    assert results[15][3] == {"pack": 2, "unpack": 2}
+    assert torch.equal(results[0][0], results[15][0]) and torch.equal(results[0][1], results[15][1])
+    for g0, g1 in zip(results[0][2], results[15][2]):
+        assert torch.equal(g0, g1)
