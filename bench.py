@@ -198,7 +198,7 @@ class TimedBackend:
     TIMED = ("conv", "conv_bwdstats", "wgrad", "apply", "gn_bwd_reduce", "gn_bwd_apply", "gn_finalize", "gn_bwd_finalize",
              "apply_gn", "gn_bwd_reduce_gn", "gn_bwd_apply_gn", "gn_bwd_fused_gn", "pack_weight", "unpack_wgrad",
              "colsum", "head_probs", "head_fwd", "head_bwd", "loss_partials", "loss_finalize", "loss_bwd", "pool_fwd",
-             "pool_bwd", "pack_many", "unpack_many", "dropout_masks", "metric_finalize", "adam_step")
+             "pool_bwd", "pack_many", "pack_launch", "unpack_many", "dropout_masks", "metric_finalize", "adam_step")
 
     def __init__(self, inner):
         self.inner, self.records, self.tag = inner, [], "other"

@@ -161,6 +161,13 @@ class PackedWeight:
         self.t, self.code, self.src, self.kind, self.which, self.dims = t, code, src, kind, which, dims
 
 
+class _PackPlan:
+    __slots__ = ("outs", "table", "ndesc", "blocks", "anchor")
+
+    def __init__(self, outs, table, ndesc, blocks, anchor):
+        self.outs, self.table, self.ndesc, self.blocks, self.anchor = outs, table, ndesc, blocks, anchor
+
+
 class CudaBackend:
     name = "cuda-sm100a"
 
@@ -258,31 +265,39 @@ class CudaBackend:
                                                      s_t, s_k, s_n2, s_n1, flip, dev, st))
         return PackedWeight(out, code, w, kind, which, dims)
 
-    def _table_to_device(self, descs, device, stream=None):
-        """ctypes descriptor array -> device tensor, written by a kernel that receives the bytes as ARGUMENTS (no
-        host-to-device memcpy: see b200seg_upload_table).  The tensor is allocated on the CURRENT stream; with
-        ``stream`` the writing kernel goes to that torch stream after it has waited for the current one."""
+    def _table_alloc(self, descs, device):
+        """ctypes descriptor array -> (device tensor allocated on the current stream, host bytes, size)"""
         arr = (PackDesc * len(descs))(*descs)
         nbytes = C.sizeof(arr)
         pad = (nbytes + 15) // 16 * 16
         buf = (C.c_char * pad)()
         C.memmove(buf, arr, nbytes)
-        devt = torch.empty(pad, dtype=torch.uint8, device=device)
-        dev = device.index if device.index is not None else torch.cuda.current_device()
-        if stream is not None:
-            stream.wait_stream(torch.cuda.current_stream(dev))
-        st = stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        return torch.empty(pad, dtype=torch.uint8, device=device), buf, pad
+
+    def _table_upload(self, tab, st):
+        """the descriptor bytes reach the device as kernel ARGUMENTS (no host-to-device memcpy: b200seg_upload_table)"""
+        devt, buf, pad = tab
+        dev = devt.device.index if devt.device.index is not None else torch.cuda.current_device()
         self._check(self.lib.b200seg_upload_table(C.cast(buf, C.c_void_p), pad, devt.data_ptr(), dev, st))
+        self._keep_tables.append(devt)
+        if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
+            self._keep_tables.pop(0)
         return devt
 
-    def pack_many(self, reqs, stream=None):
-        """reqs: [(w, kind, which, dtype, dims, vox)] -> [PackedWeight]: ONE launch for all operands.
-        ``stream``: launch on that torch stream instead of the current one (the outputs are still allocated on the
-        current stream; the launch is ordered after everything the current stream has enqueued so far, and the CALLER
-        makes the consumer wait for ``stream``)."""
-        if not reqs:
-            return []
-        dev, st = self._ds(reqs[0][0])
+    def _launch_stream(self, dev, stream, after):
+        """raw handle of the stream a launch goes to: the current one, or ``stream`` once it has been made to wait for
+        the event ``after`` (default: for everything the current stream has enqueued so far)"""
+        if stream is None:
+            return torch.cuda.current_stream(dev).cuda_stream
+        if after is not None:
+            stream.wait_event(after)
+        else:
+            stream.wait_stream(torch.cuda.current_stream(dev))
+        return stream.cuda_stream
+
+    def pack_plan(self, reqs):
+        """reqs: [(w, kind, which, dtype, dims, vox)] -> plan: the outputs and the descriptor table are ALLOCATED (on the
+        current stream), nothing is launched.  ``plan.outs`` is the [PackedWeight] list."""
         descs, outs, blocks = [], [], 0
         for (w, kind, which, dtype, dims, vox) in reqs:
             shape, code, args = self._pack_plan(w, kind, which, dtype, dims, True, vox)
@@ -295,14 +310,22 @@ class CudaBackend:
                                       flip, blocks, nb))
                 blocks += nb
             outs.append(PackedWeight(out, code, w, kind, which, dims))
-        # every allocation above and the table's are made on the current stream; only the two launches move
-        table = self._table_to_device(descs, reqs[0][0].device, stream)
-        self._check(self.lib.b200seg_pack_weights_multi(table.data_ptr(), len(descs), blocks, dev,
-                                                        stream.cuda_stream if stream is not None else st))
-        self._keep_tables.append(table)
-        if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
-            self._keep_tables.pop(0)
-        return outs
+        return _PackPlan(outs, self._table_alloc(descs, reqs[0][0].device), len(descs), blocks, reqs[0][0])
+
+    def pack_launch(self, plan, stream=None, after=None):
+        """the two launches of a plan (table upload + ONE pack kernel), on the current stream or on ``stream`` (which
+        first waits for the event ``after``, or for the current stream); the CALLER makes consumers wait for ``stream``"""
+        dev, _ = self._ds(plan.anchor)
+        st = self._launch_stream(dev, stream, after)
+        table = self._table_upload(plan.table, st)
+        self._check(self.lib.b200seg_pack_weights_multi(table.data_ptr(), plan.ndesc, plan.blocks, dev, st))
+        return plan.outs
+
+    def pack_many(self, reqs, stream=None):
+        """reqs: [(w, kind, which, dtype, dims, vox)] -> [PackedWeight]: ONE launch for all operands."""
+        if not reqs:
+            return []
+        return self.pack_launch(self.pack_plan(reqs), stream)
 
     def unpack_many(self, items, stream=None):
         """items: [(dwp [t][k][n], grad view)] -> parameter-layout gradients, ONE launch (on ``stream`` if given, after
@@ -316,12 +339,10 @@ class CudaBackend:
             nb = max(1, min(256, (dwp.numel() + 4095) // 4096))
             descs.append(PackDesc(dwp.data_ptr(), grad.data_ptr(), 1, t, k * t, 0, F32, t, k, n, 1, 0, blocks, nb))
             blocks += nb
-        table = self._table_to_device(descs, items[0][0].device, stream)
-        self._check(self.lib.b200seg_unpack_wgrads_multi(table.data_ptr(), len(descs), blocks, dev,
-                                                         stream.cuda_stream if stream is not None else st))
-        self._keep_tables.append(table)
-        if len(self._keep_tables) > 64 and not torch.cuda.is_current_stream_capturing():
-            self._keep_tables.pop(0)
+        tab = self._table_alloc(descs, items[0][0].device)
+        st = self._launch_stream(dev, stream, None)
+        table = self._table_upload(tab, st)
+        self._check(self.lib.b200seg_unpack_wgrads_multi(table.data_ptr(), len(descs), blocks, dev, st))
 
     def unpack_wgrad(self, dwp, grad, kind, dims):
         t, k, n = dwp.shape

@@ -474,11 +474,9 @@ static int loss_blocks(long long nvox_, int device) {
 static dim3 sample_grid(long long vox, int N, int device) {
   // blocks per SM over the whole grid: every block ends in one fp64 atomic per partial sum (15 for two classes) on
   // the SAME few addresses, so more blocks buy load parallelism and pay in serialised atomics (B200SEG_LOSS_BPS: A/B)
-  static const int bps = [] {
-    const char* e = getenv("B200SEG_LOSS_BPS");
-    const int v = e ? atoi(e) : 0;
-    return v >= 1 && v <= 16 ? v : 8;
-  }();
+  const char* e = getenv("B200SEG_LOSS_BPS");          // read per call (host side, once per launch): in-process A/B
+  const int v = e ? atoi(e) : 0;
+  const int bps = v >= 1 && v <= 16 ? v : 8;
   long long per = (vox + 256 * 4 - 1) / (256 * 4);
   long long cap = ((long long)num_sms(device) * bps + N - 1) / N;
   if (per > cap) per = cap;

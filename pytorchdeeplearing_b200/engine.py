@@ -144,6 +144,7 @@ class Engine:
         self._fwd_side = None                  # side stream carrying forward-time work (late pack, zero fills) not yet joined
         self._late: set = set()                # weights whose forward operand comes from the side-stream pack
         self._pre_bwd = None                   # (flat, z64 buffer, z32 buffer) zeroed during forward for backward
+        self._deferred = None                  # (side, fork event, pack plan, zero buffers) not launched yet
 
     # ---------------------------------------------------------------- allocation helpers
     def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
@@ -170,23 +171,14 @@ class Engine:
         else:
             self._z32 = None
 
-    def _zero_ahead(self, n: int, device) -> None:
-        """OV_ZERO: allocate what backward wants zero-filled (flat gradient bucket, both accumulator arenas) now and
-        fill it on the side stream, under the forward kernels; joined with the late pack (``_join_fwd_side``)."""
-        side = _side_stream(device)
-        if side is None:
-            return
+    def _zero_ahead_alloc(self, n: int, device):
+        """OV_ZERO: what backward wants zero-filled (flat gradient bucket, both accumulator arenas) is allocated during
+        forward and filled on the side stream under the forward kernels (``_launch_deferred``)."""
         n64, n32 = self._arena_sizes(n, True)
         total = sum(p.numel() for p in self.P.values())
-        bufs = (torch.empty(total, dtype=torch.float32, device=device),
+        return (torch.empty(total, dtype=torch.float32, device=device),
                 torch.empty(max(1, n64), dtype=torch.float64, device=device),
                 torch.empty(max(1, n32), dtype=torch.float32, device=device))
-        side.wait_stream(torch.cuda.current_stream(device))     # after the allocations: whoever held the blocks is done
-        with torch.cuda.stream(side):
-            for b in bufs:
-                b.zero_()
-        self._pre_bwd = bufs
-        self._fwd_side = side
 
     def _next_mask(self) -> Optional[Tensor]:
         if self.masks is None:
@@ -198,12 +190,16 @@ class Engine:
     def _prepack(self, specs, need_grad: bool, n_early: int = 0) -> None:
         """ONE launch packs every conv operand of the step (forward and data-gradient layouts).
         specs: [(wname, kind, vox_out, vox_in, needs_dgrad)].  With OV_PACK the forward operands of the first
-        ``n_early`` specs are packed by a small launch on the main stream and everything else by a second launch on the
-        side stream, which the main stream joins at the first use of one of those operands."""
+        ``n_early`` specs are packed by a small launch on the main stream; everything else is packed by a second launch
+        on the side stream, enqueued right AFTER the first convolution of the pass (so that convolution's CTAs are
+        dispatched first and the pack fills what it leaves free) and joined at the first use of one of its operands."""
         reqs, keys, late_reqs, late_keys = [], [], [], []
         self._tag(None)
         ov = overlap_mask()
-        split = bool(ov & OV_PACK) and 0 < n_early < len(specs)
+        dev = self.P[specs[0][0]].device
+        side = _side_stream(dev)
+        # (without a side stream -- CPU test backend, B200SEG_WGRAD_SIDE_STREAM=0 -- the same launches stay on the main stream)
+        split = bool(ov & OV_PACK) and 0 < n_early < len(specs) and hasattr(self.be, "pack_plan")
         for i, (wname, kind, vox_out, vox_in, dgrad) in enumerate(specs):
             early = not split or i < n_early
             (reqs if early else late_reqs).append((self.P[wname], kind, "fwd", self.T, self.dims, vox_out))
@@ -212,18 +208,39 @@ class Engine:
                 (late_reqs if split else reqs).append((self.P[wname], kind, "dgrad", self.T, self.dims, vox_in))
                 (late_keys if split else keys).append((wname, "dgrad"))
         self._packs = dict(zip(keys, self.be.pack_many(reqs)))
-        self._late, self._fwd_side, self._pre_bwd = set(), None, None
-        dev = specs and self.P[specs[0][0]].device
+        self._late, self._fwd_side, self._pre_bwd, self._deferred = set(), None, None, None
+        plan = bufs = None
         if late_reqs:
-            side = _side_stream(dev)
+            plan = self.be.pack_plan(late_reqs)                 # allocations now, launches deferred
+            self._packs.update(zip(late_keys, plan.outs))
+            self._late = {k[0] for k in late_keys if k[1] == "fwd"}
+        if need_grad and (ov & OV_ZERO):
+            bufs = self._pre_bwd = self._zero_ahead_alloc(self._batch, dev)
+        if plan is not None or bufs is not None:
+            fork = None
             if side is not None:
-                self._packs.update(zip(late_keys, self.be.pack_many(late_reqs, stream=side)))
-                self._late = {k[0] for k in late_keys if k[1] == "fwd"}
-                self._fwd_side = side
-            else:
-                self._packs.update(zip(late_keys, self.be.pack_many(late_reqs)))
-        if need_grad and (ov & OV_ZERO) and specs:
-            self._zero_ahead(self._batch, dev)
+                fork = torch.cuda.Event()
+                fork.record(torch.cuda.current_stream(dev))     # after the allocations: whoever held the blocks is done
+            self._deferred = (side, fork, plan, bufs)
+
+    def _launch_deferred(self) -> None:
+        side, fork, plan, bufs = self._deferred
+        self._deferred = None
+        if side is None:
+            if plan is not None:
+                self.be.pack_launch(plan)
+            for b in bufs or ():
+                b.zero_()
+            return
+        if plan is not None:
+            self.be.pack_launch(plan, stream=side, after=fork)
+        else:
+            side.wait_event(fork)
+        if bufs is not None:
+            with torch.cuda.stream(side):
+                for b in bufs:
+                    b.zero_()
+        self._fwd_side = side
 
     def _join_fwd_side(self) -> None:
         """the main stream waits for the forward-time side work (late pack, zero fills)"""
@@ -281,13 +298,17 @@ class Engine:
     def conv_raw(self, kind: int, wname: str, bname: Optional[str], x: Tensor, y: Tensor,
                  stats: Optional[Tensor] = None) -> None:
         w = self.P[wname]
-        if self._fwd_side is not None and wname in self._late:
+        if wname in self._late:
+            if self._deferred is not None:
+                self._launch_deferred()
             self._join_fwd_side()
         wpk = self._packs.get((wname, "fwd"))
         if wpk is None:
             wpk = self.be.pack_weight(w, kind, "fwd", self.T, self.dims, vox=y.numel() // (y.shape[0] * y.shape[-1]))
         bias = self.P[bname] if bname is not None else None
         self.be.conv(kind, self.dims, x, wpk, bias, y, stats, None)
+        if self._deferred is not None:
+            self._launch_deferred()                    # behind the first convolution of the pass
 
     def conv_gn(self, kind: int, wname: str, bname: Optional[str], gname: str, x: Tensor,
                 out_sp: Sequence[int], cout: int) -> Layer:
@@ -318,6 +339,8 @@ class Engine:
         """OutputTransition3d / UNet head: 1x1 conv to the classes + sigmoid/softmax (VNet3d.py:90-99).
         Inference form (``mask_threshold`` set; predict, model/modelVNet.py:655-676): the uint8 mask directly."""
         self._tag(wname)
+        if self._deferred is not None:
+            self._launch_deferred()
         self._join_fwd_side()                      # the last forward op: nothing of this pass stays un-joined
         if self.mask_threshold is not None:
             mask = torch.empty((x.shape[0],) + tuple(sp0), dtype=torch.uint8, device=x.device)

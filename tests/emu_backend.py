@@ -57,6 +57,18 @@ class EmuBackend:
     def pack_many(self, reqs):
         return [self.pack_weight(w, kind, which, dtype, dims, vox=vox) for (w, kind, which, dtype, dims, vox) in reqs]
 
+    # plan / launch split of the real backend (engine OV_PACK): the "plan" holds the packed operands, which are only
+    # handed to the engine; ``launches`` counts what a real backend would have launched
+    def pack_plan(self, reqs):
+        import types
+        return types.SimpleNamespace(outs=self.pack_many(reqs), launched=False)
+
+    def pack_launch(self, plan, stream=None, after=None):
+        assert stream is None and after is None and not plan.launched      # no streams on the CPU
+        plan.launched = True
+        self.deferred_pack_launches = getattr(self, "deferred_pack_launches", 0) + 1
+        return plan.outs
+
     def unpack_many(self, items):
         for dwp, grad in items:
             grad.copy_(dwp.permute(2, 1, 0).reshape(grad.shape))
