@@ -473,10 +473,11 @@ static int loss_blocks(long long nvox_, int device) {
 // blocks per sample for the (blocks, N) grids of the partial-sum kernels
 static dim3 sample_grid(long long vox, int N, int device) {
   // blocks per SM over the whole grid: every block ends in one fp64 atomic per partial sum (15 for two classes) on
-  // the SAME few addresses, so more blocks buy load parallelism and pay in serialised atomics (B200SEG_LOSS_BPS: A/B)
+  // the SAME few addresses, so more blocks buy load parallelism and pay in serialised atomics.  Measured on B200,
+  // VNet3d 96^3 batch 2 step (profiles/r2_overlap_ab.jsonl): 8 -> 3.145 ms, 4 -> 3.137 ms, 2 -> 3.150 ms
   const char* e = getenv("B200SEG_LOSS_BPS");          // read per call (host side, once per launch): in-process A/B
   const int v = e ? atoi(e) : 0;
-  const int bps = v >= 1 && v <= 16 ? v : 8;
+  const int bps = v >= 1 && v <= 16 ? v : 4;
   long long per = (vox + 256 * 4 - 1) / (256 * 4);
   long long cap = ((long long)num_sms(device) * bps + N - 1) / N;
   if (per > cap) per = cap;

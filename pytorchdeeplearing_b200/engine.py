@@ -69,14 +69,27 @@ OV_TAIL = 4      # backward: the weight gradient of the first input-block branch
                  # the second one (neither has a data gradient behind it)
 OV_ZERO = 8      # the zero fills backward needs (gradient bucket, accumulator arenas) are issued on the side stream
                  # during forward
-_OV_DEFAULT = "0"
+OV_ALL = OV_PACK | OV_UNPACK | OV_TAIL | OV_ZERO
 
 
-def overlap_mask() -> int:
-    try:
-        return int(os.environ.get("B200SEG_OVERLAP", _OV_DEFAULT))
-    except ValueError:
+def overlap_mask(arch: str = "vnet", dims: int = 3) -> int:
+    """``B200SEG_OVERLAP`` if set, else the measured default (one B200, A/B of CUDA-graph replays in one process,
+    ``profiles/r2_overlap_ab.jsonl``): all four options together gain 0.9 % on VNet3d 96^3 batch 2 (3.166 -> 3.137 ms
+    with the loss grid below) and 2.1 % on UNet2d 512^2 batch 8 (3.855 -> 3.769 ms) -- no single option gains on its
+    own -- and LOSE 1.9 % on UNet3d 128^3 batch 1 (3.732 -> 3.803 ms), so the 3-D UNet keeps the plain schedule.
+    Data-parallel runs keep it too: the options were validated on one GPU only."""
+    e = os.environ.get("B200SEG_OVERLAP")
+    if e is not None:
+        try:
+            return int(e) & OV_ALL
+        except ValueError:
+            return 0
+    if arch == "unet" and dims == 3:
         return 0
+    from . import runtime
+    if runtime.dp_state()[0]:
+        return 0
+    return OV_ALL
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
@@ -145,6 +158,7 @@ class Engine:
         self._late: set = set()                # weights whose forward operand comes from the side-stream pack
         self._pre_bwd = None                   # (flat, z64 buffer, z32 buffer) zeroed during forward for backward
         self._deferred = None                  # (side, fork event, pack plan, zero buffers) not launched yet
+        self._ov = 0                           # scheduling options of this pass (overlap_mask), fixed at forward
 
     # ---------------------------------------------------------------- allocation helpers
     def new(self, like: Tensor, sp: Sequence[int], c: int, dtype=None) -> Tensor:
@@ -195,7 +209,7 @@ class Engine:
         dispatched first and the pack fills what it leaves free) and joined at the first use of one of its operands."""
         reqs, keys, late_reqs, late_keys = [], [], [], []
         self._tag(None)
-        ov = overlap_mask()
+        ov = self._ov
         dev = self.P[specs[0][0]].device
         side = _side_stream(dev)
         # (without a side stream -- CPU test backend, B200SEG_WGRAD_SIDE_STREAM=0 -- the same launches stay on the main stream)
@@ -226,6 +240,15 @@ class Engine:
     def _launch_deferred(self) -> None:
         side, fork, plan, bufs = self._deferred
         self._deferred = None
+        tag = getattr(self.be, "tag", None)
+        self._tag(None)                                         # per-block tables book the pack under "other"
+        try:
+            self._launch_deferred_inner(side, fork, plan, bufs)
+        finally:
+            if tag is not None:
+                self.be.tag = tag
+
+    def _launch_deferred_inner(self, side, fork, plan, bufs) -> None:
         if side is None:
             if plan is not None:
                 self.be.pack_launch(plan)
@@ -253,7 +276,7 @@ class Engine:
         """OV_UNPACK (single GPU; data parallel has ``_flush_bucket`` at the same place): the weight gradients
         accumulated so far go to parameter layout on the side stream, in stream order behind the kernels that produced
         them; the unpack at the end of backward only handles the remaining (small, full-resolution) layers."""
-        if not (overlap_mask() & OV_UNPACK) or self.bucket_hook is not None or not self._unpack_list:
+        if not (self._ov & OV_UNPACK) or self.bucket_hook is not None or not self._unpack_list:
             return
         items, self._unpack_list = self._unpack_list, []
         side = self._side
@@ -526,7 +549,7 @@ class Engine:
             specs.append((name + ".up_conv.weight", UP, vox[i], vox[i + 1], True))
             specs.append((name + ".conv.weight", K1, vox[i], vox[i], True))
             specs += [(f"{name}.ops.{j}.conv1.weight", K3, vox[i], vox[i], True) for j in range(nops)]
-        self._batch = n
+        self._batch, self._ov = n, overlap_mask("vnet", dims)
         self._prepack(specs, need_grad, n_early=5)         # in_tr (2) + down_tr32 (down conv + 2 ops)
 
         # ---- InputTransition3d (VNet3d.py:34-43): one bn1 serves both branches
@@ -612,7 +635,7 @@ class Engine:
                 self._flush_bucket("down_tr256.down_conv.weight")
                 self._early_unpack()
         La, Lb = sv["in_tr"]
-        self.bwd_layer(La, g, False, side_wgrad=bool(overlap_mask() & OV_TAIL))
+        self.bwd_layer(La, g, False, side_wgrad=bool(self._ov & OV_TAIL))
         self.bwd_layer(Lb, g, False)
         self._finish_backward()
         return flat
@@ -653,7 +676,7 @@ class Engine:
             specs.append((f"upconv{i + 1}.weight", UP, vox[i], vox[i + 1], True))
             specs.append((f"decoder{i + 1}.dec{i + 1}conv1.weight", K3, vox[i], vox[i], True))
             specs.append((f"decoder{i + 1}.dec{i + 1}conv2.weight", K3, vox[i], vox[i], True))
-        self._batch = n
+        self._batch, self._ov = n, overlap_mask("unet", dims)
         self._prepack(specs, need_grad, n_early=2)         # encoder1
 
         def block(mod: str, name: str, h: Tensor, sp, co: int, dst: Tensor):

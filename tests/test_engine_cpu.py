@@ -470,3 +470,12 @@ def test_overlap_options_change_launch_grouping_not_results(kind, cin, ncls, spa
     assert torch.equal(results[0][0], results[15][0]) and torch.equal(results[0][1], results[15][1])
     for g0, g1 in zip(results[0][2], results[15][2]):
         assert torch.equal(g0, g1)
+
+
+def test_overlap_defaults_follow_the_measurements(monkeypatch):
+    from pytorchdeeplearing_b200 import engine
+    monkeypatch.delenv("B200SEG_OVERLAP", raising=False)
+    assert engine.overlap_mask("vnet", 3) == engine.OV_ALL and engine.overlap_mask("unet", 2) == engine.OV_ALL
+    assert engine.overlap_mask("unet", 3) == 0               # measured slower on UNet3d 128^3
+    monkeypatch.setenv("B200SEG_OVERLAP", "5")
+    assert engine.overlap_mask("unet", 3) == 5
