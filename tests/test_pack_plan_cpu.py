@@ -116,3 +116,38 @@ def test_kmajor_tensor_core_layout(kind, cin, cout, dims, which):
     else:
         want = w3.permute(2, 1, 0)                     # [t][B][A]
     assert tuple(got.shape) == tuple(want.shape) and torch.equal(got, want.contiguous())
+
+
+# ------------------------------------------------------------------------------------------------ tensor descriptors
+def test_tensor_descriptor_of_channel_pitch_views():
+    """``_desc``: every kernel argument is an (N,D,H,W,C) view with unit channel stride and a channel pitch ld >= C
+     -- the halves of a skip-concat buffer, unit-depth 2-D tensors, single-voxel levels."""
+    cat = torch.zeros(2, 4, 6, 8, 32, dtype=torch.bfloat16)
+    left, right = cat[..., :16], cat[..., 16:]
+    for view, off in ((left, 0), (right, 16)):
+        d = _abi._desc(view)
+        assert (d.n, d.d, d.h, d.w, d.c, d.ld, d.dtype) == (2, 4, 6, 8, 16, 32, BF16)
+        assert d.ptr == cat.data_ptr() + off * cat.element_size()
+    d = _abi._desc(torch.zeros(3, 1, 5, 7, 4))                         # 2-D net: unit depth, fp32, dense
+    assert (d.n, d.d, d.h, d.w, d.c, d.ld, d.dtype) == (3, 1, 5, 7, 4, 4, F32)
+    d = _abi._desc(torch.zeros(2, 1, 1, 1, 64)[..., 32:])               # one voxel per sample: pitch from the batch stride
+    assert (d.c, d.ld) == (32, 64)
+    d = _abi._desc(torch.zeros(1, 1, 1, 1, 8))                          # nothing to infer a pitch from: dense
+    assert (d.c, d.ld) == (8, 8)
+    x = torch.zeros(2, 1, 4, 6, 8).permute(0, 2, 3, 4, 1)               # (N,1,D,H,W) network input read as NDHWC, C = 1
+    d = _abi._desc(x)
+    assert (d.n, d.d, d.h, d.w, d.c, d.ld) == (2, 4, 6, 8, 1, 1)
+    assert _abi._desc(None) is None
+
+
+def test_tensor_descriptor_rejects_what_the_kernels_cannot_address():
+    ncdhw = torch.zeros(2, 8, 4, 4, 4).permute(0, 2, 3, 4, 1)[..., :8]
+    assert ncdhw.stride(-1) != 1
+    with pytest.raises(ValueError):
+        _abi._desc(ncdhw)                                               # channel stride != 1
+    with pytest.raises(ValueError):
+        _abi._desc(torch.zeros(2, 4, 4, 4, 8)[:, :, ::2])               # strided rows
+    with pytest.raises(ValueError):
+        _abi._desc(torch.zeros(4, 4, 4, 8))                             # not 5-D
+    with pytest.raises(TypeError):
+        _abi._desc(torch.zeros(1, 2, 2, 2, 8, dtype=torch.float16))     # only fp32 / bf16 activations
