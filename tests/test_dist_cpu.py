@@ -14,10 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, arch, q):
+def _worker(rank, world, port, arch, q, ov=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if ov is not None:
+        os.environ["B200SEG_OVERLAP"] = ov           # side-stream scheduling options forced on under data parallelism
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle
@@ -70,12 +72,15 @@ def _worker(rank, world, port, arch, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("arch", ["vnet3d", "unet2d"])
-def test_two_rank_sharding_matches_global_batch(arch):
+@pytest.mark.parametrize("arch,ov", [("vnet3d", None), ("unet2d", None), ("vnet3d", "15")])
+def test_two_rank_sharding_matches_global_batch(arch, ov):
+    """``ov``: by default data-parallel runs keep the plain schedule (engine.overlap_mask); the forced case checks that
+    the options' host logic (split pack, gradient bucket allocated and zeroed during forward, bucket flush in place of
+    the early unpack) still reproduces the global-batch result"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, arch, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if ov else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, arch, q, ov)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
